@@ -1,0 +1,473 @@
+// d2q9.cuh — device-side building blocks of the fused D2Q9 step (sm_100a).
+//
+// What one reference time step computes for a cell is specified in SURVEY.md Appendix D
+// (restating src/main.cu:96-114 of Carabalone/cuda-lbm).  The reference runs it as nine
+// full-grid kernels over three population buffers; here it is one register-resident
+// function chain per cell:  pull -> boundary -> moments -> force -> collide -> store,
+// over ONE in-place SoA population buffer addressed with the AA pattern:
+//
+//   even step (local):      g_q(x) = A[q][x]               store f*_q -> A[opp q][x]
+//   odd  step (neighbour):  g_q(x) = A[opp q][x - c_q]     store f*_q -> A[q][x + c_q]
+//
+// Every cell reads exactly the nine slots it later overwrites, so no second buffer and no
+// inter-thread hazard exists.  Arithmetic follows the reference's formulas (cited per
+// function) in pure fp32 with FMA contraction; parity is to fp32 round-off (tests state it).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace lbm {
+
+constexpr int Q = 9;
+
+// quirk bits (include/lbm_b200.h)
+constexpr int QK_D1 = 1, QK_D2 = 2, QK_D3 = 4, QK_D7 = 8, QK_D8 = 16, QK_D11 = 32;
+
+// BC_flag values — reference src/core/lbm_constants.cuh:377-397
+enum : int {
+    FLUID = 0, BOUNCE_BACK = 1, ZOU_HE_TOP = 2, ZOU_HE_LEFT = 3, CYLINDER = 6, ZG_OUTFLOW = 7,
+    PRESSURE_OUTLET = 8, REGULARIZED_INLET_TOP = 9, REGULARIZED_BOUNCE_BACK = 11,
+    REGULARIZED_BOUNCE_BACK_CORNER = 12
+};
+constexpr uint8_t FLAG_IBM = 0x80;   // node lies in a marker stencil: force comes from ibm_force[]
+constexpr uint8_t FLAG_MASK = 0x1f;
+
+// lattice tables — reference src/core/lbm_constants.cuh:13-31 (h_C, h_OPP, h_weights)
+__host__ __device__ __forceinline__ constexpr int cx(int q) { return (q == 1 || q == 5 || q == 8) ? 1 : ((q == 3 || q == 6 || q == 7) ? -1 : 0); }
+__host__ __device__ __forceinline__ constexpr int cy(int q) { return (q == 2 || q == 5 || q == 6) ? 1 : ((q == 4 || q == 7 || q == 8) ? -1 : 0); }
+__host__ __device__ __forceinline__ constexpr int opp(int q) { return q == 0 ? 0 : (q <= 4 ? ((q + 1) % 4) + 1 : ((q - 3) % 4) + 5); }
+__host__ __device__ __forceinline__ constexpr float wq(int q) { return q == 0 ? 4.0f / 9.0f : (q <= 4 ? 1.0f / 9.0f : 1.0f / 36.0f); }
+static_assert(opp(1) == 3 && opp(2) == 4 && opp(3) == 1 && opp(4) == 2 && opp(5) == 7 && opp(6) == 8 && opp(7) == 5 && opp(8) == 6, "OPP");
+
+struct Params {
+    float* A[Q];            // slot planes, each (ny_local+2) rows of nx floats; row 0 / ny_local+1 are ghost rows
+    float* A0[2];           // rest-population plane used at odd / even timesteps (same pointer unless QK_D1)
+    int nx, ny;             // global grid
+    int y0, nyl;            // slab rows [y0, y0+nyl)
+    int px, py;             // periodic axes
+    int wrap_y;             // world==1 && periodic_y: y wraps inside the slab (ghost rows unused)
+    int t;                  // timestep being computed (1-based); parity selects the AA phase
+    int quirks;
+    int coll;
+    const uint8_t* flags;   // nyl*nx, nullptr = all FLUID and no IBM
+    float omega;
+    float S[Q];
+    float u_max;
+    float fx, fy;           // uniform body force
+    const float2* force_plane;   // optional per-node body force (local nodes)
+    float* ring;            // [2][perim][9] post-collision populations of domain-edge nodes of the last two steps
+    int perim;
+    const long long* nbr_nodes; const float* nbr_g; int nbr_count;   // neighbour-reading BC nodes (sorted global ids) and the neighbour's post-stream g
+    const long long* ibm_nodes; const float2* ibm_force; int ibm_count;
+    const float* avg;       // 3 floats: grid means of rho, rho|u|, |Pi| (OptimalAdapter)
+    float* partials;        // per-block partial sums (3 per block) or nullptr
+    float* rho_out; float2* u_out;     // macroscopic output of this step (nullptr = none)
+};
+
+__device__ __forceinline__ long long rowoff(const Params& p, int yl) { return (long long)(yl + 1) * p.nx; }
+
+// Source / destination coordinate of a streaming hop with the reference's per-axis periodic wrap
+// (src/core/streaming/streaming.cu:13-21).  Returns false when the hop leaves a non-periodic domain.
+// yl is a local row; rows -1 and nyl address the ghost rows of a slab interface.
+__device__ __forceinline__ bool hop(const Params& p, int& x, int& yl, int dx, int dy) {
+    bool ok = true;
+    if (dx != 0) {
+        x += dx;
+        if (x < 0) { if (p.px) x += p.nx; else ok = false; }
+        else if (x >= p.nx) { if (p.px) x -= p.nx; else ok = false; }
+    }
+    if (dy != 0) {
+        yl += dy;
+        int yg = p.y0 + yl;
+        if (yg < 0) { if (p.py) { if (p.wrap_y) yl += p.ny; } else ok = false; }
+        else if (yg >= p.ny) { if (p.py) { if (p.wrap_y) yl -= p.ny; } else ok = false; }
+    }
+    return ok;
+}
+
+// index into the edge ring, or -1 for nodes not on a non-periodic domain edge
+__device__ __forceinline__ int edge_index(const Params& p, int x, int yg) {
+    if (!p.py) { if (yg == 0) return x; if (yg == p.ny - 1) return p.nx + x; }
+    if (!p.px) { if (x == 0) return 2 * p.nx + yg; if (x == p.nx - 1) return 2 * p.nx + p.ny + yg; }
+    return -1;
+}
+
+// Post-stream populations of node (x, yl): step 1 of Appendix D (stream_node, streaming.cu:5-33).
+// Slots whose source lies outside a non-periodic domain are "undelivered": the reference leaves the
+// node's own post-collision value of two steps ago there (its two-buffer swap), reproduced from the ring.
+template <bool ODD>
+__device__ __forceinline__ int pull(const Params& p, int x, int yl, float g[Q]) {
+    const int gen = p.t & 1;
+    const long long row = rowoff(p, yl);
+    g[0] = p.A0[gen][row + x];
+    if (!ODD) {
+#pragma unroll
+        for (int q = 1; q < Q; q++) g[q] = p.A[q][row + x];
+    } else {
+#pragma unroll
+        for (int q = 1; q < Q; q++) {
+            int xs = x, ys = yl;
+            bool ok = hop(p, xs, ys, -cx(q), -cy(q));
+            g[q] = ok ? p.A[opp(q)][rowoff(p, ys) + xs] : 0.0f;
+        }
+    }
+    const int yg = p.y0 + yl;
+    const int e = edge_index(p, x, yg);
+    if (e >= 0) {
+        const bool ex0 = !p.px && x == 0, ex1 = !p.px && x == p.nx - 1;
+        const bool ey0 = !p.py && yg == 0, ey1 = !p.py && yg == p.ny - 1;
+        const float* r = p.ring + ((long long)gen * p.perim + e) * Q;
+#pragma unroll
+        for (int q = 1; q < Q; q++) {
+            bool und = (ex0 && cx(q) > 0) || (ex1 && cx(q) < 0) || (ey0 && cy(q) > 0) || (ey1 && cy(q) < 0);
+            if (und) g[q] = r[q];
+        }
+    }
+    return e;
+}
+
+template <bool ODD>
+__device__ __forceinline__ void push(const Params& p, int x, int yl, int e, const float f[Q]) {
+    const int gen = p.t & 1;
+    const long long row = rowoff(p, yl);
+    p.A0[gen][row + x] = f[0];
+    if (!ODD) {
+#pragma unroll
+        for (int q = 1; q < Q; q++) p.A[opp(q)][row + x] = f[q];
+    } else {
+#pragma unroll
+        for (int q = 1; q < Q; q++) {
+            int xd = x, yd = yl;
+            bool ok = hop(p, xd, yd, cx(q), cy(q));
+            if (ok) p.A[q][rowoff(p, yd) + xd] = f[q];
+        }
+    }
+    if (e >= 0) {
+        float* r = p.ring + ((long long)gen * p.perim + e) * Q;
+#pragma unroll
+        for (int q = 0; q < Q; q++) r[q] = f[q];
+    }
+}
+
+// ------------------------------------------------------------------ equilibrium
+// second-order f_eq — reference src/core/equilibrium/equilibrium.cu:5-39 (pure fp32 here)
+__device__ __forceinline__ float feq(int q, float rho, float ux, float uy, float usq15) {
+    float cu = cx(q) * ux + cy(q) * uy;
+    return wq(q) * rho * (1.0f + 3.0f * cu + 4.5f * cu * cu - usq15);
+}
+
+struct Moments { float rho, ux, uy, pxx, pxy, pyy; };
+
+// uncorrected_macroscopics_kernel<2> — reference src/core/macroscopics/macroscopics.cu:5-38
+__device__ __forceinline__ Moments moments(const float g[Q]) {
+    Moments m;
+    m.rho = g[0] + g[1] + g[2] + g[3] + g[4] + g[5] + g[6] + g[7] + g[8];
+    float jx = (g[1] - g[3]) + (g[5] - g[6]) + (g[8] - g[7]);
+    float jy = (g[2] - g[4]) + (g[5] - g[8]) + (g[6] - g[7]);
+    float inv = 1.0f / m.rho;
+    m.ux = jx * inv; m.uy = jy * inv;
+    float d = g[5] + g[6] + g[7] + g[8];
+    m.pxx = g[1] + g[3] + d;
+    m.pyy = g[2] + g[4] + d;
+    m.pxy = (g[5] - g[6]) + (g[7] - g[8]);
+    return m;
+}
+__device__ __forceinline__ float pi_norm(const Moments& m) { return sqrtf(m.pxx * m.pxx + 2.0f * m.pxy * m.pxy + m.pyy * m.pyy); }
+
+// ------------------------------------------------------------------ boundary functors (Appendix D step 2)
+__device__ __forceinline__ int find_sorted(const long long* a, int n, long long key) {
+    int lo = 0, hi = n - 1;
+    while (lo <= hi) { int mid = (lo + hi) >> 1; long long v = a[mid]; if (v == key) return mid; if (v < key) lo = mid + 1; else hi = mid - 1; }
+    return -1;
+}
+
+// BounceBack<2>::apply — reference src/functors/boundaryConditions/bbDomainBoundary.cuh:22-49
+__device__ __forceinline__ void bc_bounce_back(const Params& p, float g[Q], int x, int yg) {
+    const bool raw = (p.quirks & QK_D11) != 0;
+#pragma unroll
+    for (int i = 1; i < Q; i++) {
+        int xn = x + cx(i), yn = yg + cy(i);
+        bool xb = (xn < 0 || xn >= p.nx) && (raw || !p.px);
+        bool yb = (yn < 0 || yn >= p.ny) && (raw || !p.py);
+        if (xb || yb) g[opp(i)] = g[i];
+    }
+}
+
+// ZouHe::apply_left — reference src/functors/boundaryConditions/zouHeInflow.cuh:9-33
+__device__ __forceinline__ void bc_zou_he_left(const Params& p, float g[Q]) {
+    const float ux = p.u_max;
+    float a = (p.quirks & QK_D3) ? g[2] : g[3];
+    float rho = (g[0] + g[2] + g[4] + 2.0f * (a + g[6] + g[7])) / (1.0f - ux);
+    g[1] = g[3] + (2.0f / 3.0f) * rho * ux;
+    g[5] = g[7] - 0.5f * (g[2] - g[4]) + (1.0f / 6.0f) * rho * ux;
+    g[8] = g[6] + 0.5f * (g[2] - g[4]) + (1.0f / 6.0f) * rho * ux;
+}
+
+// ZouHe::apply_top — reference zouHeInflow.cuh:36-50 (u = (u_max, 0))
+__device__ __forceinline__ void bc_zou_he_top(const Params& p, float g[Q]) {
+    const float ux = p.u_max;
+    float rho = g[0] + g[1] + g[3] + 2.0f * (g[2] + g[5] + g[6]);
+    g[4] = g[2];
+    float d13 = g[1] - g[3];
+    g[7] = g[5] + 0.5f * d13 - 0.5f * rho * ux;
+    g[8] = g[6] - 0.5f * d13 + 0.5f * rho * ux;
+}
+
+// CylinderBoundary::apply — reference src/functors/boundaryConditions/cylinderBoundary.cuh:22-34
+__device__ __forceinline__ void bc_cylinder(float g[Q]) {
+    float t;
+    t = g[1]; g[1] = g[3]; g[3] = t;
+    t = g[2]; g[2] = g[4]; g[4] = t;
+    t = g[5]; g[5] = g[7]; g[7] = t;
+    t = g[6]; g[6] = g[8]; g[8] = t;
+}
+
+// ZG_OutflowBoundary<2>::apply — reference src/functors/boundaryConditions/zeroGradientOutflow.cuh:9-59
+__device__ __forceinline__ void bc_zg_outflow(const Params& p, float g[Q], const float* nb, int x, int yg) {
+    int n0 = 0, n1 = 0;
+    if (x == 0) n0 = 1; else if (x == p.nx - 1) n0 = -1; else if (yg == 0) n1 = 1; else if (yg == p.ny - 1) n1 = -1; else return;
+#pragma unroll
+    for (int i = 0; i < Q; i++) if (cx(i) * n0 + cy(i) * n1 > 0) g[i] = nb[i];
+}
+
+// PressureOutlet::apply — reference src/functors/boundaryConditions/pressureOutlet.cuh:7-42
+__device__ __forceinline__ void bc_pressure_outlet(float g[Q], const float* nb) {
+    float h[Q];
+#pragma unroll
+    for (int i = 0; i < Q; i++) h[i] = nb[i];
+    Moments m = moments(h);
+    float usq15 = 1.5f * (m.ux * m.ux + m.uy * m.uy);
+#pragma unroll
+    for (int i = 0; i < Q; i++) g[i] = feq(i, 1.0f, m.ux, m.uy, usq15);
+}
+
+// tail shared by RegularizedInlet::apply_top (regularizedInlet.cuh:42-67) and
+// RegularizedBounceBack::apply (regularizedBounceBack.cuh:68-96): Pi(1) from all nine f, then f = f_eq + f_neq
+__device__ __forceinline__ void regularize(float g[Q], const float fe[Q], float rho, float ux, float uy) {
+    const float cs2 = 1.0f / 3.0f;
+    float d = g[5] + g[6] + g[7] + g[8];
+    float Pxx = g[1] + g[3] + d - (cs2 * rho + rho * ux * ux);
+    float Pyy = g[2] + g[4] + d - (cs2 * rho + rho * uy * uy);
+    float Pxy = (g[5] - g[6]) + (g[7] - g[8]) - rho * ux * uy;
+#pragma unroll
+    for (int q = 0; q < Q; q++) {
+        float Qxx = cx(q) * cx(q) - cs2, Qyy = cy(q) * cy(q) - cs2, Qxy = (float)(cx(q) * cy(q));
+        g[q] = fe[q] + (wq(q) * 4.5f) * (Qxx * Pxx + Qyy * Pyy + 2.0f * Qxy * Pxy);
+    }
+}
+
+// RegularizedInlet::apply_top — reference src/functors/boundaryConditions/regularizedInlet.cuh:15-69
+__device__ __forceinline__ void bc_regularized_inlet_top(const Params& p, float g[Q]) {
+    const float ux = p.u_max, uy = 0.0f;
+    float rho = g[0] + g[1] + g[3] + 2.0f * (g[2] + g[5] + g[6]);
+    float fe[Q];
+    float usq15 = 1.5f * ux * ux;
+#pragma unroll
+    for (int q = 0; q < Q; q++) fe[q] = feq(q, rho, ux, uy, usq15);
+#pragma unroll
+    for (int q = 0; q < Q; q++) if (cy(q) < 0) g[q] = fe[q] + (g[opp(q)] - fe[opp(q)]);
+    regularize(g, fe, rho, ux, uy);
+}
+
+// RegularizedBounceBack::apply — reference src/functors/boundaryConditions/regularizedBounceBack.cuh:13-99
+__device__ __forceinline__ void bc_regularized_bb(const Params& p, float g[Q], int x, int yg) {
+    int sx = 0, sy = 0;       // sign of the unknown directions along the wall normal
+    if (x == 0) sx = 1; else if (x == p.nx - 1) sx = -1; else if (yg == 0) sy = 1; else if (yg == p.ny - 1) sy = -1;
+    bool unk[Q];
+    unk[0] = false;
+#pragma unroll
+    for (int i = 1; i < Q; i++) unk[i] = (cx(i) * sx + cy(i) * sy) > 0;
+    float rho = 0.0f;
+#pragma unroll
+    for (int i = 0; i < Q; i++) if (!unk[i]) rho += (unk[opp(i)] ? 2.0f : 1.0f) * g[i];
+    float fe[Q];
+#pragma unroll
+    for (int q = 0; q < Q; q++) fe[q] = wq(q) * rho;        // u = 0
+#pragma unroll
+    for (int q = 0; q < Q; q++) if (unk[q]) g[q] = fe[q] + (g[opp(q)] - fe[opp(q)]);
+    regularize(g, fe, rho, 0.0f, 0.0f);
+}
+
+// RegularizedCornerBounceBack::apply — reference regularizedBounceBack.cuh:107-221; nb = post-stream
+// populations of the diagonal interior node (:136-147)
+__device__ __forceinline__ void bc_regularized_corner(const Params& p, float g[Q], const float* nb, int x, int yg) {
+    const bool left = x == 0, right = x == p.nx - 1, bottom = yg == 0, top = yg == p.ny - 1;
+    if (!((left || right) && (bottom || top))) return;
+    float rho = 0.0f;
+#pragma unroll
+    for (int i = 0; i < Q; i++) rho += nb[i];
+#pragma unroll
+    for (int i = 1; i < Q; i++) {
+        bool unk = (left && cx(i) > 0) || (right && cx(i) < 0) || (bottom && cy(i) > 0) || (top && cy(i) < 0);
+        if (unk) g[i] = wq(i) * rho - (g[opp(i)] - wq(opp(i)) * rho);       // minus sign: :164
+    }
+    // regularize_distributions :192-221 — Pi from f - f_eq (u = 0)
+    const float cs2 = 1.0f / 3.0f;
+    float n[Q];
+#pragma unroll
+    for (int q = 0; q < Q; q++) n[q] = g[q] - wq(q) * rho;
+    float d = n[5] + n[6] + n[7] + n[8];
+    float Pxx = n[1] + n[3] + d, Pyy = n[2] + n[4] + d, Pxy = (n[5] - n[6]) + (n[7] - n[8]);
+#pragma unroll
+    for (int q = 0; q < Q; q++) {
+        float Qxx = cx(q) * cx(q) - cs2, Qyy = cy(q) * cy(q) - cs2, Qxy = (float)(cx(q) * cy(q));
+        g[q] = wq(q) * rho + (wq(q) * 4.5f) * (Qxx * Pxx + Qyy * Pyy + 2.0f * Qxy * Pxy);
+    }
+}
+
+// boundaries_kernel_2D switch — reference src/core/boundaries/boundaries.cuh:29-83
+__device__ __forceinline__ void apply_bc(const Params& p, int flag, float g[Q], int x, int yg) {
+    switch (flag) {
+    case BOUNCE_BACK: bc_bounce_back(p, g, x, yg); break;
+    case ZOU_HE_TOP: bc_zou_he_top(p, g); break;
+    case ZOU_HE_LEFT: bc_zou_he_left(p, g); break;
+    case CYLINDER: bc_cylinder(g); break;
+    case REGULARIZED_INLET_TOP: bc_regularized_inlet_top(p, g); break;
+    case REGULARIZED_BOUNCE_BACK: bc_regularized_bb(p, g, x, yg); break;
+    case ZG_OUTFLOW:
+    case PRESSURE_OUTLET:
+    case REGULARIZED_BOUNCE_BACK_CORNER: {
+        int k = find_sorted(p.nbr_nodes, p.nbr_count, (long long)yg * p.nx + x);
+        if (k < 0) break;
+        const float* nb = p.nbr_g + (long long)k * Q;
+        if (flag == ZG_OUTFLOW) bc_zg_outflow(p, g, nb, x, yg);
+        else if (flag == PRESSURE_OUTLET) bc_pressure_outlet(g, nb);
+        else bc_regularized_corner(p, g, nb, x, yg);
+        break;
+    }
+    default: break;
+    }
+}
+
+// ------------------------------------------------------------------ collision operators (Appendix D step 7)
+// BGK<2>::apply — reference src/core/collision/BGK/BGK.cuh:13-51 (Guo forcing)
+__device__ __forceinline__ void collide_bgk(const Params& p, float g[Q], float rho, float ux, float uy, float Fx, float Fy) {
+    const float om = p.omega, k = 1.0f - 0.5f * om;
+    const float usq15 = 1.5f * (ux * ux + uy * uy);
+    const float uF = ux * Fx + uy * Fy;
+#pragma unroll
+    for (int q = 0; q < Q; q++) {
+        float cu = cx(q) * ux + cy(q) * uy;
+        float cF = cx(q) * Fx + cy(q) * Fy;
+        float fe = wq(q) * rho * (1.0f + 3.0f * cu + 4.5f * cu * cu - usq15);
+        float ft = (wq(q) * k) * (3.0f * (cF - uF) + 9.0f * cu * cF);
+        g[q] = g[q] - om * (g[q] - fe) + ft;
+    }
+}
+
+// MRT<2>::apply + compute_forcing_term — reference src/core/collision/MRT/MRT.cu:4-76, M / M^-1 of
+// lbm_constants.cuh:33-55 folded into add/sub chains; m_eq = M f_eq(rho,u) written in closed form.
+__device__ __forceinline__ void collide_mrt(const Params& p, float g[Q], float rho, float ux, float uy, float Fx, float Fy) {
+    const float sA = (g[1] + g[3]) + (g[2] + g[4]), sD = (g[5] + g[7]) + (g[6] + g[8]);
+    float m[Q];
+    m[0] = g[0] + sA + sD;
+    m[1] = -4.0f * g[0] - sA + 2.0f * sD;
+    m[2] = 4.0f * g[0] - 2.0f * sA + sD;
+    const float dx1 = g[1] - g[3], dx2 = (g[5] - g[6]) + (g[8] - g[7]);
+    const float dy1 = g[2] - g[4], dy2 = (g[5] - g[8]) + (g[6] - g[7]);
+    m[3] = dx1 + dx2;
+    m[4] = -2.0f * dx1 + dx2;
+    m[5] = dy1 + dy2;
+    m[6] = -2.0f * dy1 + dy2;
+    m[7] = (g[1] + g[3]) - (g[2] + g[4]);
+    m[8] = (g[5] + g[7]) - (g[6] + g[8]);
+    const float jx = rho * ux, jy = rho * uy, usq = ux * ux + uy * uy;
+    float me[Q] = {rho, rho * (3.0f * usq - 2.0f), rho * (1.0f - 3.0f * usq), jx, -jx, jy, -jy, rho * (ux * ux - uy * uy), rho * ux * uy};
+    const float uF = Fx * ux + Fy * uy;
+    float F[Q];
+    F[0] = 0.0f; F[1] = 6.0f * uF; F[2] = -6.0f * uF; F[3] = Fx;
+    if (p.quirks & QK_D2) { F[4] = Fy; F[5] = -Fx; } else { F[4] = -Fx; F[5] = Fy; }
+    F[6] = -Fy; F[7] = 2.0f * (Fx * ux - Fy * uy); F[8] = Fx * uy + Fy * ux;
+#pragma unroll
+    for (int k = 0; k < Q; k++) m[k] = m[k] - p.S[k] * (m[k] - me[k]) + (1.0f - 0.5f * p.S[k]) * F[k];
+    const float a = m[0] * (1.0f / 9.0f);
+    const float b1 = m[1] * (1.0f / 36.0f), b2 = m[2] * (1.0f / 36.0f);
+    const float ax = a - b1 - 2.0f * b2, dg = a + 2.0f * b1 + b2;
+    const float x6 = (m[3] - m[4]) * (1.0f / 6.0f), y6 = (m[5] - m[6]) * (1.0f / 6.0f);
+    const float xd = m[3] * (1.0f / 6.0f) + m[4] * (1.0f / 12.0f), yd = m[5] * (1.0f / 6.0f) + m[6] * (1.0f / 12.0f);
+    const float p4 = m[7] * 0.25f, q4 = m[8] * 0.25f;
+    g[0] = a - 4.0f * b1 + 4.0f * b2;
+    g[1] = ax + x6 + p4;
+    g[2] = ax + y6 - p4;
+    g[3] = ax - x6 + p4;
+    g[4] = ax - y6 - p4;
+    g[5] = dg + xd + yd + q4;
+    g[6] = dg - xd + yd - q4;
+    g[7] = dg - xd - yd + q4;
+    g[8] = dg + xd - yd - q4;
+}
+
+// OptimalAdapter::compute_higher_order_relaxation — reference src/core/collision/adapters.cuh:48-111
+__device__ __forceinline__ float optimal_rate(float rho, float jmag, float pimag, const float* avg) {
+    float ts = 0.0003f * (rho / avg[0]) - 0.00775f * (jmag / avg[1]) + 0.00016f * (pimag / avg[2]) + 0.0087f;
+    ts = ts > 0.0f ? ts : 0.005f;
+    ts = fminf(ts, 1.5f);
+    return 1.0f / (3.0f * ts + 0.5f);
+}
+
+// CM<2,Adapter>::apply — reference src/core/collision/CM/CM.cuh:27-139.  The reference accumulates the
+// nine central moments with per-direction polynomials and multiplies by an 81-entry T^-1(u)
+// (cm_matrix_inverse, :141-250, ~900 flop).  Here: raw moments (add chains) -> binomial shift by -u ->
+// relax -> shift by +u -> populations; algebraically identical (tests/test_transforms.py), ~200 flop.
+template <bool OPTIMAL>
+__device__ __forceinline__ void collide_cm(const Params& p, float g[Q], float ux, float uy, float Fx, float Fy) {
+    // raw moments m_ab = sum f cx^a cy^b
+    const float d = (g[5] + g[7]) + (g[6] + g[8]);
+    const float m00 = g[0] + ((g[1] + g[3]) + (g[2] + g[4])) + d;      // rho recomputed from f (:38-41)
+    const float m10 = (g[1] - g[3]) + ((g[5] - g[6]) + (g[8] - g[7]));
+    const float m01 = (g[2] - g[4]) + ((g[5] - g[8]) + (g[6] - g[7]));
+    const float m20 = (g[1] + g[3]) + d, m02 = (g[2] + g[4]) + d;
+    const float m11 = (g[5] + g[7]) - (g[6] + g[8]);
+    const float m21 = (g[5] + g[6]) - (g[7] + g[8]);       // sum f cx^2 cy
+    const float m12 = (g[5] + g[8]) - (g[6] + g[7]);       // sum f cx cy^2
+    const float m22 = d;
+    const float rho = m00;
+    const float ux2 = ux * ux, uy2 = uy * uy, uxuy = ux * uy;
+    // central moments about u
+    const float k10 = m10 - ux * m00, k01 = m01 - uy * m00;
+    const float k20 = m20 - 2.0f * ux * m10 + ux2 * m00;
+    const float k02 = m02 - 2.0f * uy * m01 + uy2 * m00;
+    const float k11 = m11 - ux * m01 - uy * m10 + uxuy * m00;
+    const float a21 = m21 - 2.0f * ux * m11 + ux2 * m01;            // sum f (cx-ux)^2 cy
+    const float a12 = m12 - 2.0f * uy * m11 + uy2 * m10;            // sum f cx (cy-uy)^2
+    const float k21 = a21 - uy * k20, k12 = a12 - ux * k02;
+    const float k22 = m22 - 2.0f * uy * m21 + uy2 * m20 - 2.0f * ux * a12 + ux2 * k02;
+    const float cs2 = 1.0f / 3.0f;
+    float k[Q] = {m00, k10, k01, k20 + k02, k20 - k02, k11, k21, k12, k22};
+    const float keq[Q] = {rho, 0.0f, 0.0f, 2.0f * rho * cs2, 0.0f, 0.0f, 0.0f, 0.0f, rho * cs2 * cs2};
+    const float F[Q] = {0.0f, Fx, Fy, 0.0f, 0.0f, 0.0f, Fy * cs2, Fx * cs2, 0.0f};
+    float hi = 1.0f;
+    if (OPTIMAL) {
+        float pimag = sqrtf(m20 * m20 + 2.0f * m11 * m11 + m02 * m02);
+        float jmag = sqrtf(ux2 + uy2) * rho;
+        hi = optimal_rate(rho, jmag, pimag, p.avg);
+    }
+#pragma unroll
+    for (int i = 0; i < Q; i++) {
+        float r = (OPTIMAL && i > 5) ? hi : p.S[i];                // AdapterBase::is_higher_order, adapters.cuh:8-13
+        k[i] = k[i] - r * (k[i] - keq[i]) + (1.0f - 0.5f * r) * F[i];
+    }
+    // back to raw moments (shift by +u)
+    const float c00 = k[0], c10 = k[1], c01 = k[2];
+    const float c20 = 0.5f * (k[3] + k[4]), c02 = 0.5f * (k[3] - k[4]);
+    const float c11 = k[5], c21 = k[6], c12 = k[7], c22 = k[8];
+    const float r10 = c10 + ux * c00, r01 = c01 + uy * c00;
+    const float r20 = c20 + 2.0f * ux * c10 + ux2 * c00;
+    const float r02 = c02 + 2.0f * uy * c01 + uy2 * c00;
+    const float r11 = c11 + ux * c01 + uy * c10 + uxuy * c00;
+    const float b12 = c12 + 2.0f * uy * c11 + uy2 * c10;            // sum f (cx-ux)(cy)^2
+    const float r21 = c21 + 2.0f * ux * c11 + ux2 * c01 + uy * r20;
+    const float r12 = b12 + ux * r02;
+    const float r22 = c22 + 2.0f * uy * c21 + uy2 * c20 + 2.0f * ux * b12 + ux2 * r02;
+    g[0] = c00 - r20 - r02 + r22;
+    g[1] = 0.5f * ((r10 + r20) - (r12 + r22));
+    g[3] = 0.5f * ((r20 - r10) + (r12 - r22));
+    g[2] = 0.5f * ((r01 + r02) - (r21 + r22));
+    g[4] = 0.5f * ((r02 - r01) + (r21 - r22));
+    g[5] = 0.25f * ((r11 + r22) + (r21 + r12));
+    g[6] = 0.25f * ((r22 - r11) + (r21 - r12));
+    g[7] = 0.25f * ((r11 + r22) - (r21 + r12));
+    g[8] = 0.25f * ((r22 - r11) - (r21 - r12));
+}
+
+}  // namespace lbm

@@ -1,0 +1,686 @@
+// engine.cu — host side of the B200-native D2Q9 engine and its C ABI (include/lbm_b200.h).
+//
+// Replaces the reference's LBM<2> host methods (src/core/lbm.cuh:33-382) and IBMManager<2>
+// (src/IBM/IBMManager.cuh:31-253).  Data layout in HBM (per slab of ny_local rows):
+//   populations  9 planes x (ny_local+2) rows x nx fp32   (SoA, rows 0 / ny_local+1 = slab ghost rows)
+//   rest plane   +1 plane when LBM_QK_D1_STALE_F0 (the reference's two interleaved f0 histories)
+//   flags        1 byte / node (only when a scenario has non-FLUID nodes or bodies)
+//   edge ring    2 x (2nx+2ny) x 9 fp32: post-collision values of domain-edge nodes (undelivered slots)
+//   macroscopics rho (1 plane) + u (AoS float2), allocated on first request
+#include <cuda_runtime.h>
+#include <thrust/device_ptr.h>
+#include <thrust/sort.h>
+#include <thrust/unique.h>
+#include <thrust/binary_search.h>
+#include <thrust/copy.h>
+#include <thrust/execution_policy.h>
+#include <thrust/iterator/counting_iterator.h>
+#include <thrust/sequence.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+#include "../../include/lbm_b200.h"
+#include "kernels.cuh"
+
+using namespace lbm;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+#define CU(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e__ = (call);                                                                      \
+        if (e__ != cudaSuccess)                                                                        \
+            return fail(LBM_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__) + " (" + __FILE__ + ":" + std::to_string(__LINE__) + ")"); \
+    } while (0)
+
+struct lbm_handle {
+    lbm_config cfg{};
+    int y0 = 0, nyl = 0;
+    long long nloc = 0;
+    size_t plane = 0;               // floats per slot plane
+    cudaStream_t stream = nullptr, own_stream = nullptr;
+    float* pop = nullptr;           // 9 (+1) planes
+    int nplanes = 9;
+    uint8_t* flags = nullptr;
+    float2* force_plane = nullptr;
+    float* ring = nullptr; int perim = 0;
+    long long* nbr_nodes = nullptr; long long* nbr_src = nullptr; float* nbr_g = nullptr; int nbr_count = 0;
+    // IBM
+    std::vector<float> h_pts;
+    float* d_pts = nullptr; long long* ibm_nodes = nullptr; int* sten_idx = nullptr; float* sten_w = nullptr;
+    int* csr_row = nullptr; int* csr_k = nullptr; float* csr_w = nullptr;
+    float* ibm_rho = nullptr; float2* ibm_uprev = nullptr; float2* ibm_lagF = nullptr; float2* ibm_force = nullptr;
+    int np = 0, ibm_count = 0, ibm_ss = 4;
+    // adapter
+    float* partials = nullptr; long long n_partials = 0; double* sums = nullptr; float* avg = nullptr; int avg_for_ts = -1; int pre_for_ts = -1;
+    // macroscopics
+    float* rho_out = nullptr; float2* u_out = nullptr; int macros_ts = -1;
+    double* mass_acc = nullptr;
+    int timestep = 0;
+    long long launches = 0;
+    long long bytes = 0;
+    float omega = 1.0f;
+};
+
+template <typename T>
+static cudaError_t dmalloc(lbm_handle* h, T** p, size_t count) {
+    cudaError_t e = cudaMalloc((void**)p, count * sizeof(T));
+    if (e == cudaSuccess) h->bytes += (long long)(count * sizeof(T));
+    return e;
+}
+
+static Params make_params(lbm_handle* h, int t) {
+    Params p{};
+    for (int q = 0; q < Q; q++) p.A[q] = h->pop + (size_t)q * h->plane;
+    p.A0[0] = p.A[0];
+    p.A0[1] = (h->nplanes == 10) ? h->pop + (size_t)9 * h->plane : p.A[0];
+    p.nx = h->cfg.nx; p.ny = h->cfg.ny; p.y0 = h->y0; p.nyl = h->nyl;
+    p.px = h->cfg.periodic_x; p.py = h->cfg.periodic_y;
+    p.wrap_y = (h->cfg.world == 1 && h->cfg.periodic_y) ? 1 : 0;
+    p.t = t; p.quirks = h->cfg.quirks; p.coll = h->cfg.collision;
+    p.flags = h->flags;
+    p.omega = h->omega;
+    for (int i = 0; i < Q; i++) p.S[i] = h->cfg.S[i];
+    p.u_max = h->cfg.u_max; p.fx = h->cfg.force_x; p.fy = h->cfg.force_y;
+    p.force_plane = h->force_plane;
+    p.ring = h->ring; p.perim = h->perim;
+    p.nbr_nodes = h->nbr_nodes; p.nbr_g = h->nbr_g; p.nbr_count = h->nbr_count;
+    p.ibm_nodes = h->ibm_nodes; p.ibm_force = h->ibm_force; p.ibm_count = h->ibm_count;
+    p.avg = h->avg; p.partials = nullptr; p.rho_out = nullptr; p.u_out = nullptr;
+    return p;
+}
+
+static dim3 grid_of(const lbm_handle* h) { return dim3((h->cfg.nx + BX - 1) / BX, h->nyl); }
+
+extern "C" const char* lbm_last_error(void) { return g_err.c_str(); }
+
+extern "C" int lbm_default_config(lbm_config* c) {
+    if (!c) return fail(LBM_ERR_INVALID, "cfg is NULL");
+    memset(c, 0, sizeof(*c));
+    c->nx = 128; c->ny = 128; c->collision = LBM_BGK;
+    c->viscosity = 1.0f / 6.0f;                      // ScenarioTrait::viscosity, scenario.cuh:35
+    float om = 1.0f / (3 * c->viscosity + 0.5f);
+    float S[9] = {0.f, om, om, 0.f, om, 0.f, om, om, om};   // scenario.cuh:47-57
+    memcpy(c->S, S, sizeof(S));
+    c->u_max = 0.1f;                                 // scenario.cuh:59
+    c->quirks = LBM_QK_REFERENCE; c->adapter_mode = LBM_ADAPTER_EXACT;
+    c->world = 1;
+    return LBM_OK;
+}
+
+extern "C" int lbm_destroy(lbm_handle* h) {
+    if (!h) return LBM_OK;
+    cudaSetDevice(h->cfg.device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    void* ptrs[] = {h->pop, h->flags, h->force_plane, h->ring, h->nbr_nodes, h->nbr_src, h->nbr_g, h->d_pts, h->ibm_nodes,
+                    h->sten_idx, h->sten_w, h->csr_row, h->csr_k, h->csr_w, h->ibm_rho, h->ibm_uprev, h->ibm_lagF, h->ibm_force,
+                    h->partials, h->sums, h->avg, h->rho_out, h->u_out, h->mass_acc};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+    return LBM_OK;
+}
+
+extern "C" int lbm_create(const lbm_config* cfg, lbm_handle** out) {
+    if (!cfg || !out) return fail(LBM_ERR_INVALID, "NULL argument");
+    *out = nullptr;
+    if (cfg->nx < 3 || cfg->ny < 3) return fail(LBM_ERR_INVALID, "grid must be at least 3x3");
+    if (cfg->collision < LBM_BGK || cfg->collision > LBM_CM_OPTIMAL) return fail(LBM_ERR_INVALID, "unknown collision operator");
+    if (cfg->world < 1 || cfg->rank < 0 || cfg->rank >= cfg->world) return fail(LBM_ERR_INVALID, "bad rank/world");
+    if (cfg->ny / cfg->world < 2) return fail(LBM_ERR_INVALID, "each slab needs at least 2 rows");
+    // host asserts of LBM::init (src/core/init/init.cuh:62-64) become error returns
+    if (!(cfg->viscosity > 0.0f)) return fail(LBM_ERR_INVALID, "Negative Viscosity");
+    if (!(3 * cfg->viscosity + 0.5f > 0.5f)) return fail(LBM_ERR_INVALID, "Instability warning: tau < 0.5");
+    if (!(cfg->u_max < 0.5f)) return fail(LBM_ERR_INVALID, "Instability warning: u_max > 0.5");
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(LBM_ERR_INVALID, "no such CUDA device");
+    CU(cudaSetDevice(cfg->device));
+    lbm_handle* h = new lbm_handle();
+    h->cfg = *cfg;
+    const float tau = 3 * cfg->viscosity + 0.5f;     // viscosity_to_tau, lbm_constants.cuh:365-367
+    h->omega = 1.0f / tau;
+    // slab rows: the first (ny % world) slabs get one extra row
+    int base = cfg->ny / cfg->world, rem = cfg->ny % cfg->world;
+    h->nyl = base + (cfg->rank < rem ? 1 : 0);
+    h->y0 = cfg->rank * base + std::min(cfg->rank, rem);
+    h->nloc = (long long)h->nyl * cfg->nx;
+    h->plane = (size_t)(h->nyl + 2) * cfg->nx;
+    h->nplanes = (cfg->quirks & LBM_QK_D1_STALE_F0) ? 10 : 9;
+    cudaError_t e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete h; return fail(LBM_ERR_CUDA, cudaGetErrorString(e)); }
+    h->stream = h->own_stream;
+    h->perim = 2 * cfg->nx + 2 * cfg->ny;
+    bool ok = dmalloc(h, &h->pop, h->plane * h->nplanes) == cudaSuccess &&
+              dmalloc(h, &h->ring, (size_t)2 * h->perim * Q) == cudaSuccess &&
+              dmalloc(h, &h->sums, 3) == cudaSuccess && dmalloc(h, &h->avg, 3) == cudaSuccess &&
+              dmalloc(h, &h->mass_acc, 1) == cudaSuccess;
+    if (ok && cfg->collision == LBM_CM_OPTIMAL) {
+        dim3 g = grid_of(h);
+        h->n_partials = (long long)g.x * g.y;
+        ok = dmalloc(h, &h->partials, (size_t)3 * h->n_partials) == cudaSuccess;
+    }
+    if (!ok) { std::string m = cudaGetErrorString(cudaGetLastError()); lbm_destroy(h); return fail(LBM_ERR_CUDA, "device allocation failed: " + m); }
+    cudaMemsetAsync(h->pop, 0, h->plane * h->nplanes * sizeof(float), h->stream);
+    cudaMemsetAsync(h->ring, 0, (size_t)2 * h->perim * Q * sizeof(float), h->stream);
+    float one[3] = {1.f, 1.f, 1.f};
+    cudaMemcpyAsync(h->avg, one, sizeof(one), cudaMemcpyHostToDevice, h->stream);
+    cudaStreamSynchronize(h->stream);
+    *out = h;
+    return LBM_OK;
+}
+
+extern "C" int lbm_set_stream(lbm_handle* h, void* s) {
+    if (!h) return fail(LBM_ERR_INVALID, "NULL handle");
+    cudaSetDevice(h->cfg.device);
+    CU(cudaStreamSynchronize(h->stream));
+    h->stream = s ? (cudaStream_t)s : h->own_stream;
+    return LBM_OK;
+}
+
+static int ensure_flags(lbm_handle* h) {
+    if (h->flags) return LBM_OK;
+    CU(dmalloc(h, &h->flags, (size_t)h->nloc));
+    CU(cudaMemsetAsync(h->flags, 0, (size_t)h->nloc, h->stream));
+    return LBM_OK;
+}
+
+static int rebuild_ibm(lbm_handle* h);
+
+extern "C" int lbm_set_flags(lbm_handle* h, const int32_t* flags) {
+    if (!h || !flags) return fail(LBM_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(h->cfg.device));
+    const int nx = h->cfg.nx, ny = h->cfg.ny;
+    std::vector<uint8_t> loc((size_t)h->nloc);
+    std::vector<std::pair<long long, long long>> nbr;     // (node, source node)
+    bool any = false;
+    for (int yl = 0; yl < h->nyl; yl++)
+        for (int x = 0; x < nx; x++) {
+            int y = h->y0 + yl;
+            long long node = (long long)y * nx + x;
+            int f = flags[node];
+            if (f < 0 || f > 31) return fail(LBM_ERR_INVALID, "flag out of range");
+            loc[(size_t)yl * nx + x] = (uint8_t)f;
+            any |= (f != 0);
+            long long src = -1;
+            if (f == LBM_ZG_OUTFLOW) {                  // zeroGradientOutflow.cuh:16-42
+                int ix = x, iy = y;
+                if (x == 0) ix = 1; else if (x == nx - 1) ix = nx - 2; else if (y == 0) iy = 1; else if (y == ny - 1) iy = ny - 2; else continue;
+                src = (long long)iy * nx + ix;
+            } else if (f == LBM_PRESSURE_OUTLET) {      // pressureOutlet.cuh:10-13
+                if (x == 0) return fail(LBM_ERR_INVALID, "PRESSURE_OUTLET at x=0 has no x-1 neighbour");
+                src = (long long)y * nx + (x - 1);
+            } else if (f == LBM_REGULARIZED_BOUNCE_BACK_CORNER) {   // regularizedBounceBack.cuh:113-145
+                bool l = x == 0, r = x == nx - 1, b = y == 0, t = y == ny - 1;
+                if (!((l || r) && (b || t))) continue;
+                int dx = l ? x + 1 : x - 1, dy = b ? y + 1 : y - 1;
+                dx = std::max(1, std::min(dx, nx - 2)); dy = std::max(1, std::min(dy, ny - 2));
+                src = (long long)dy * nx + dx;
+            }
+            if (src >= 0) {
+                int sy = (int)(src / nx);
+                if (sy < h->y0 || sy >= h->y0 + h->nyl) return fail(LBM_ERR_INVALID, "boundary node reads a neighbour owned by another slab");
+                nbr.emplace_back(node, src);
+            }
+        }
+    if (h->nbr_nodes) { cudaFree(h->nbr_nodes); cudaFree(h->nbr_src); cudaFree(h->nbr_g); h->nbr_nodes = h->nbr_src = nullptr; h->nbr_g = nullptr; }
+    h->nbr_count = (int)nbr.size();
+    if (any || h->np > 0) {
+        int rc = ensure_flags(h); if (rc) return rc;
+        CU(cudaMemcpyAsync(h->flags, loc.data(), loc.size(), cudaMemcpyHostToDevice, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+    } else if (h->flags) {
+        CU(cudaMemsetAsync(h->flags, 0, (size_t)h->nloc, h->stream));
+    }
+    if (h->nbr_count) {
+        std::sort(nbr.begin(), nbr.end());
+        std::vector<long long> a(nbr.size()), b(nbr.size());
+        for (size_t i = 0; i < nbr.size(); i++) { a[i] = nbr[i].first; b[i] = nbr[i].second; }
+        CU(dmalloc(h, &h->nbr_nodes, a.size())); CU(dmalloc(h, &h->nbr_src, a.size())); CU(dmalloc(h, &h->nbr_g, a.size() * Q));
+        CU(cudaMemcpy(h->nbr_nodes, a.data(), a.size() * 8, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(h->nbr_src, b.data(), b.size() * 8, cudaMemcpyHostToDevice));
+    }
+    if (h->np > 0) return rebuild_ibm(h);       // re-mark the IBM bit
+    return LBM_OK;
+}
+
+extern "C" int lbm_set_body_force(lbm_handle* h, float fx, float fy) {
+    if (!h) return fail(LBM_ERR_INVALID, "NULL handle");
+    h->cfg.force_x = fx; h->cfg.force_y = fy;
+    return LBM_OK;
+}
+
+extern "C" int lbm_set_force_field(lbm_handle* h, const float* force_aos) {
+    if (!h) return fail(LBM_ERR_INVALID, "NULL handle");
+    CU(cudaSetDevice(h->cfg.device));
+    if (!force_aos) { if (h->force_plane) { cudaFree(h->force_plane); h->force_plane = nullptr; } return LBM_OK; }
+    if (!h->force_plane) CU(dmalloc(h, &h->force_plane, (size_t)h->nloc));
+    CU(cudaMemcpy(h->force_plane, force_aos + (size_t)2 * h->y0 * h->cfg.nx, (size_t)h->nloc * sizeof(float2), cudaMemcpyHostToDevice));
+    return LBM_OK;
+}
+
+// ------------------------------------------------------------------ IBM structure, built on the GPU
+__global__ void mark_ibm_kernel(uint8_t* flags, const long long* nodes, int n, long long node0, int set) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    long long ln = nodes[i] - node0;
+    if (set) flags[ln] |= FLAG_IBM; else flags[ln] &= (uint8_t)~FLAG_IBM;
+}
+__global__ void csr_fill_kernel(const int* order, const int* sten_idx_flat, const float* sten_w, int ss, int n, int* csr_k, float* csr_w) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    int s = order[e];
+    csr_k[e] = s / ss; csr_w[e] = sten_w[s];
+}
+struct not_neg_i { __host__ __device__ bool operator()(int v) const { return v >= 0; } };
+struct fix_neg_slots { const long long* n; int* i; __device__ void operator()(int s) const { if (n[s] < 0) i[s] = -1; } };
+struct gather_idx { const int* idx; const int* ord; int* out; __device__ void operator()(int e) const { out[e] = idx[ord[e]]; } };
+
+static int rebuild_ibm(lbm_handle* h) {
+    CU(cudaSetDevice(h->cfg.device));
+    if (h->cfg.world != 1) return fail(LBM_ERR_INVALID, "immersed bodies are supported on a single slab only (SURVEY.md 8e: cross-face stencils deferred)");
+    auto pol = thrust::cuda::par.on(h->stream);
+    if (h->ibm_nodes && h->flags && h->ibm_count) {
+        mark_ibm_kernel<<<(h->ibm_count + 255) / 256, 256, 0, h->stream>>>(h->flags, h->ibm_nodes, h->ibm_count, (long long)h->y0 * h->cfg.nx, 0);
+        h->launches++;
+    }
+    void* old[] = {h->d_pts, h->ibm_nodes, h->sten_idx, h->sten_w, h->csr_row, h->csr_k, h->csr_w, h->ibm_rho, h->ibm_uprev, h->ibm_lagF, h->ibm_force};
+    CU(cudaStreamSynchronize(h->stream));
+    for (void* p : old) if (p) cudaFree(p);
+    h->d_pts = nullptr; h->ibm_nodes = nullptr; h->sten_idx = nullptr; h->sten_w = nullptr; h->csr_row = nullptr; h->csr_k = nullptr; h->csr_w = nullptr;
+    h->ibm_rho = nullptr; h->ibm_uprev = nullptr; h->ibm_lagF = nullptr; h->ibm_force = nullptr;
+    h->np = (int)(h->h_pts.size() / 2); h->ibm_count = 0;
+    if (h->np == 0) return LBM_OK;
+    const int np = h->np;
+    const bool two = (h->cfg.quirks & LBM_QK_D8_IBM_2X2) != 0;
+    const int w = two ? 2 : 4, lo = two ? 0 : -1, ss = w * w;
+    h->ibm_ss = ss;
+    const int nslots = np * ss;
+    long long* sten_node = nullptr; long long* keys = nullptr; int* order = nullptr; int* node_of = nullptr;
+    CU(dmalloc(h, &h->d_pts, (size_t)2 * np));
+    CU(cudaMemcpyAsync(h->d_pts, h->h_pts.data(), (size_t)2 * np * 4, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMalloc(&sten_node, (size_t)nslots * 8)); CU(cudaMalloc(&keys, (size_t)nslots * 8));
+    CU(cudaMalloc(&order, (size_t)nslots * 4)); CU(cudaMalloc(&node_of, (size_t)nslots * 4));
+    CU(dmalloc(h, &h->sten_w, (size_t)nslots)); CU(dmalloc(h, &h->sten_idx, (size_t)nslots));
+    ibm_stencil_kernel<<<(np + 127) / 128, 128, 0, h->stream>>>(h->d_pts, np, h->cfg.nx, h->cfg.ny, lo, w, sten_node, h->sten_w);
+    h->launches++;
+    // unique sorted node list
+    CU(cudaMemcpyAsync(keys, sten_node, (size_t)nslots * 8, cudaMemcpyDeviceToDevice, h->stream));
+    thrust::device_ptr<long long> kp(keys);
+    thrust::sort(pol, kp, kp + nslots);
+    auto kend = thrust::unique(pol, kp, kp + nslots);
+    int nuniq = (int)(kend - kp);
+    long long first = 0;
+    CU(cudaMemcpyAsync(&first, keys, 8, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    int skip = first < 0 ? 1 : 0;           // the -1 marker of out-of-domain slots sorts first
+    h->ibm_count = nuniq - skip;
+    if (h->ibm_count <= 0) { h->ibm_count = 0; cudaFree(sten_node); cudaFree(keys); cudaFree(order); cudaFree(node_of); return LBM_OK; }
+    CU(dmalloc(h, &h->ibm_nodes, (size_t)h->ibm_count));
+    CU(cudaMemcpyAsync(h->ibm_nodes, keys + skip, (size_t)h->ibm_count * 8, cudaMemcpyDeviceToDevice, h->stream));
+    // compact index of every stencil slot (-1 where the slot is outside the domain)
+    thrust::device_ptr<long long> np_(h->ibm_nodes), sn(sten_node);
+    thrust::device_ptr<int> si(h->sten_idx);
+    thrust::lower_bound(pol, np_, np_ + h->ibm_count, sn, sn + nslots, si);
+    // slots with node -1 get index 0 from lower_bound: overwrite with -1
+    thrust::for_each(pol, thrust::counting_iterator<int>(0), thrust::counting_iterator<int>(nslots), fix_neg_slots{sten_node, h->sten_idx});
+    // CSR node <- (marker, weight): stable sort of the valid slots by compact node index keeps markers ascending
+    thrust::device_ptr<int> op(order), nf(node_of);
+    auto oend = thrust::copy_if(pol, thrust::counting_iterator<int>(0), thrust::counting_iterator<int>(nslots), si, op, not_neg_i());
+    int nvalid = (int)(oend - op);
+    thrust::for_each(pol, thrust::counting_iterator<int>(0), thrust::counting_iterator<int>(nvalid), gather_idx{h->sten_idx, order, node_of});
+    thrust::stable_sort_by_key(pol, nf, nf + nvalid, op);
+    CU(dmalloc(h, &h->csr_row, (size_t)h->ibm_count + 1)); CU(dmalloc(h, &h->csr_k, (size_t)nvalid)); CU(dmalloc(h, &h->csr_w, (size_t)nvalid));
+    thrust::device_ptr<int> rp(h->csr_row);
+    thrust::lower_bound(pol, nf, nf + nvalid, thrust::counting_iterator<int>(0), thrust::counting_iterator<int>(h->ibm_count + 1), rp);
+    csr_fill_kernel<<<(nvalid + 255) / 256, 256, 0, h->stream>>>(order, h->sten_idx, h->sten_w, ss, nvalid, h->csr_k, h->csr_w);
+    h->launches++;
+    CU(dmalloc(h, &h->ibm_rho, (size_t)h->ibm_count)); CU(dmalloc(h, &h->ibm_uprev, (size_t)h->ibm_count));
+    CU(dmalloc(h, &h->ibm_lagF, (size_t)np)); CU(dmalloc(h, &h->ibm_force, (size_t)h->ibm_count));
+    int rc = ensure_flags(h); if (rc) return rc;
+    mark_ibm_kernel<<<(h->ibm_count + 255) / 256, 256, 0, h->stream>>>(h->flags, h->ibm_nodes, h->ibm_count, (long long)h->y0 * h->cfg.nx, 1);
+    h->launches++;
+    CU(cudaStreamSynchronize(h->stream));
+    cudaFree(sten_node); cudaFree(keys); cudaFree(order); cudaFree(node_of);
+    CU(cudaGetLastError());
+    return LBM_OK;
+}
+
+extern "C" int lbm_add_body(lbm_handle* h, const float* pts, int32_t n) {
+    if (!h || (!pts && n > 0) || n < 0) return fail(LBM_ERR_INVALID, "bad body");
+    h->h_pts.insert(h->h_pts.end(), pts, pts + (size_t)2 * n);
+    return rebuild_ibm(h);
+}
+
+// ------------------------------------------------------------------ init
+static int ensure_macros(lbm_handle* h) {
+    if (h->rho_out) return LBM_OK;
+    CU(dmalloc(h, &h->rho_out, (size_t)h->nloc)); CU(dmalloc(h, &h->u_out, (size_t)h->nloc));
+    return LBM_OK;
+}
+
+extern "C" int lbm_reserve_macroscopics(lbm_handle* h) {
+    if (!h) return fail(LBM_ERR_INVALID, "NULL handle");
+    CU(cudaSetDevice(h->cfg.device));
+    return ensure_macros(h);
+}
+
+extern "C" int lbm_init_fields_device(lbm_handle* h, const float* d_rho, const float* d_u) {
+    if (!h || !d_rho || !d_u) return fail(LBM_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(h->cfg.device));
+    int rc = ensure_macros(h); if (rc) return rc;
+    Params p = make_params(h, 0);
+    p.rho_out = h->rho_out; p.u_out = h->u_out;
+    init_fields_kernel<<<grid_of(h), BX, 0, h->stream>>>(p, d_rho, (const float2*)d_u);
+    h->launches++;
+    CU(cudaGetLastError());
+    h->timestep = 0; h->macros_ts = 0; h->avg_for_ts = -1; h->pre_for_ts = -1;
+    return LBM_OK;
+}
+
+extern "C" int lbm_init_fields_local(lbm_handle* h, const float* rho, const float* u) {
+    if (!h || !rho || !u) return fail(LBM_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(h->cfg.device));
+    // staging in the macroscopic planes themselves: init_fields_kernel reads rho/u and writes the same values back
+    int rc = ensure_macros(h); if (rc) return rc;
+    CU(cudaMemcpyAsync(h->rho_out, rho, (size_t)h->nloc * 4, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->u_out, u, (size_t)h->nloc * 8, cudaMemcpyHostToDevice, h->stream));
+    return lbm_init_fields_device(h, h->rho_out, (const float*)h->u_out);
+}
+
+extern "C" int lbm_init_fields(lbm_handle* h, const float* rho, const float* u) {
+    if (!h || !rho || !u) return fail(LBM_ERR_INVALID, "NULL argument");
+    size_t off = (size_t)h->y0 * h->cfg.nx;
+    return lbm_init_fields_local(h, rho + off, u + 2 * off);
+}
+
+extern "C" int lbm_init_taylor_green(lbm_handle* h, float nu, float u0) {
+    if (!h) return fail(LBM_ERR_INVALID, "NULL handle");
+    CU(cudaSetDevice(h->cfg.device));
+    Params p = make_params(h, 0);
+    if (h->rho_out) { p.rho_out = h->rho_out; p.u_out = h->u_out; }
+    init_taylor_green_kernel<<<grid_of(h), BX, 0, h->stream>>>(p, nu, u0);
+    h->launches++;
+    CU(cudaGetLastError());
+    h->timestep = 0; h->macros_ts = h->rho_out ? 0 : -1; h->avg_for_ts = -1; h->pre_for_ts = -1;
+    return LBM_OK;
+}
+
+extern "C" int lbm_set_populations(lbm_handle* h, const float* f, const float* fb) {
+    if (!h || !f) return fail(LBM_ERR_INVALID, "NULL argument");
+    if (h->timestep & 1) return fail(LBM_ERR_STATE, "lbm_set_populations needs an even timestep");
+    CU(cudaSetDevice(h->cfg.device));
+    if (!fb) fb = f;
+    float *df = nullptr, *dfb = nullptr;
+    size_t off = (size_t)h->y0 * h->cfg.nx * Q, cnt = (size_t)h->nloc * Q;
+    CU(cudaMalloc(&df, cnt * 4)); CU(cudaMalloc(&dfb, cnt * 4));
+    CU(cudaMemcpyAsync(df, f + off, cnt * 4, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(dfb, fb + off, cnt * 4, cudaMemcpyHostToDevice, h->stream));
+    Params p = make_params(h, h->timestep);
+    set_populations_kernel<<<grid_of(h), BX, 0, h->stream>>>(p, df, dfb);
+    h->launches++;
+    CU(cudaStreamSynchronize(h->stream));
+    cudaFree(df); cudaFree(dfb);
+    h->macros_ts = -1; h->avg_for_ts = -1; h->pre_for_ts = -1;
+    return LBM_OK;
+}
+
+extern "C" int lbm_get_populations(lbm_handle* h, float* f) {
+    if (!h || !f) return fail(LBM_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(h->cfg.device));
+    float* df = nullptr;
+    size_t cnt = (size_t)h->nloc * Q;
+    CU(cudaMalloc(&df, cnt * 4));
+    Params p = make_params(h, h->timestep);
+    if (h->timestep & 1) get_populations_kernel<true><<<grid_of(h), BX, 0, h->stream>>>(p, df);
+    else get_populations_kernel<false><<<grid_of(h), BX, 0, h->stream>>>(p, df);
+    h->launches++;
+    CU(cudaMemcpyAsync(f + (size_t)h->y0 * h->cfg.nx * Q, df, cnt * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    cudaFree(df);
+    return LBM_OK;
+}
+
+// ------------------------------------------------------------------ the time step
+template <int COLL, bool ODD>
+static void launch_step(lbm_handle* h, const Params& p, bool general) {
+    if (general) step_kernel<COLL, ODD, true><<<grid_of(h), BX, 0, h->stream>>>(p);
+    else step_kernel<COLL, ODD, false><<<grid_of(h), BX, 0, h->stream>>>(p);
+}
+template <bool ODD>
+static void launch_step_coll(lbm_handle* h, const Params& p, bool general) {
+    switch (h->cfg.collision) {
+    case LBM_BGK: launch_step<C_BGK, ODD>(h, p, general); break;
+    case LBM_MRT: launch_step<C_MRT, ODD>(h, p, general); break;
+    case LBM_CM: launch_step<C_CM, ODD>(h, p, general); break;
+    default: launch_step<C_CMOPT, ODD>(h, p, general); break;
+    }
+}
+
+// nbr gather + IBM (+ moments pre-pass) for step t; idempotent per timestep
+static int pre_passes(lbm_handle* h, int t, bool want_moments) {
+    const bool odd = (t & 1) != 0;
+    Params p = make_params(h, t);
+    if (h->pre_for_ts != t) {
+        if (h->nbr_count) {
+            if (odd) nbr_gather_kernel<true><<<(h->nbr_count + 127) / 128, 128, 0, h->stream>>>(p, h->nbr_src, h->nbr_g, h->nbr_count);
+            else nbr_gather_kernel<false><<<(h->nbr_count + 127) / 128, 128, 0, h->stream>>>(p, h->nbr_src, h->nbr_g, h->nbr_count);
+            h->launches++;
+        }
+        if (h->ibm_count) {
+            IbmData d{h->np, h->ibm_count, h->ibm_ss, h->ibm_nodes, h->sten_idx, h->sten_w, h->csr_row, h->csr_k, h->csr_w,
+                      h->ibm_rho, h->ibm_uprev, h->ibm_lagF, h->ibm_force};
+            if (odd) ibm_kernel<true><<<1, 1024, 0, h->stream>>>(p, d); else ibm_kernel<false><<<1, 1024, 0, h->stream>>>(p, d);
+            h->launches++;
+        }
+        h->pre_for_ts = t;
+    }
+    if (want_moments) {
+        const double inv_n = 1.0 / ((double)h->cfg.nx * (double)h->cfg.ny);
+        Params pm = p; pm.partials = h->partials;
+        if (odd) moments_kernel<true><<<grid_of(h), BX, 0, h->stream>>>(pm); else moments_kernel<false><<<grid_of(h), BX, 0, h->stream>>>(pm);
+        reduce_partials_kernel<<<1, 256, 0, h->stream>>>(h->partials, h->n_partials, h->sums, h->avg, inv_n, h->cfg.world == 1);
+        h->launches += 2;
+        if (h->cfg.world == 1) h->avg_for_ts = t;
+    }
+    return LBM_OK;
+}
+
+static int one_step(lbm_handle* h, bool want_macros) {
+    const int t = h->timestep + 1;
+    const bool odd = (t & 1) != 0;
+    const bool general = h->flags != nullptr || h->force_plane != nullptr || !h->cfg.periodic_x || !h->cfg.periodic_y;
+    const bool opt = h->cfg.collision == LBM_CM_OPTIMAL;
+    const bool need_moments = opt && h->avg_for_ts != t;
+    if (need_moments && h->cfg.world > 1)
+        return fail(LBM_ERR_STATE, "OptimalAdapter on several slabs: call lbm_adapter_prepass, all-reduce lbm_get_moment_sums, lbm_set_moment_sums before lbm_step");
+    int rc = pre_passes(h, t, need_moments); if (rc) return rc;
+    Params p = make_params(h, t);
+    const bool lagged = opt && h->cfg.adapter_mode == LBM_ADAPTER_LAGGED;
+    if (lagged) p.partials = h->partials;
+    if (want_macros) { rc = ensure_macros(h); if (rc) return rc; p.rho_out = h->rho_out; p.u_out = h->u_out; }
+    if (odd) launch_step_coll<true>(h, p, general); else launch_step_coll<false>(h, p, general);
+    h->launches++;
+    if (lagged) {
+        const double inv_n = 1.0 / ((double)h->cfg.nx * (double)h->cfg.ny);
+        reduce_partials_kernel<<<1, 256, 0, h->stream>>>(h->partials, h->n_partials, h->sums, h->avg, inv_n, h->cfg.world == 1);
+        h->launches++;
+        if (h->cfg.world == 1) h->avg_for_ts = t + 1;
+    }
+    h->timestep = t;
+    if (want_macros) h->macros_ts = t;
+    return LBM_OK;
+}
+
+extern "C" int lbm_adapter_prepass(lbm_handle* h) {
+    if (!h) return fail(LBM_ERR_INVALID, "NULL handle");
+    if (h->cfg.collision != LBM_CM_OPTIMAL) return LBM_OK;
+    CU(cudaSetDevice(h->cfg.device));
+    int rc = pre_passes(h, h->timestep + 1, true); if (rc) return rc;
+    CU(cudaGetLastError());
+    return LBM_OK;
+}
+
+static int run_steps(lbm_handle* h, int n, bool macros_last) {
+    if (!h) return fail(LBM_ERR_INVALID, "NULL handle");
+    if (n < 0) return fail(LBM_ERR_INVALID, "nsteps < 0");
+    if (h->cfg.world > 1 && n > 1) return fail(LBM_ERR_INVALID, "world > 1: step one at a time and exchange halos in between");
+    CU(cudaSetDevice(h->cfg.device));
+    for (int i = 0; i < n; i++) {
+        int rc = one_step(h, macros_last && i == n - 1);
+        if (rc) return rc;
+    }
+    CU(cudaGetLastError());
+    return LBM_OK;
+}
+
+extern "C" int lbm_step(lbm_handle* h, int32_t n) { return run_steps(h, n, false); }
+extern "C" int lbm_step_with_macroscopics(lbm_handle* h, int32_t n) { return run_steps(h, n, true); }
+
+extern "C" int lbm_sync(lbm_handle* h) {
+    if (!h) return fail(LBM_ERR_INVALID, "NULL handle");
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaStreamSynchronize(h->stream));
+    return LBM_OK;
+}
+
+extern "C" int lbm_get_macroscopics_device(lbm_handle* h, const float** rho, const float** u) {
+    if (!h || !rho || !u) return fail(LBM_ERR_INVALID, "NULL argument");
+    if (h->macros_ts != h->timestep || !h->rho_out)
+        return fail(LBM_ERR_STATE, "macroscopics of the current timestep were not produced: run the last step with lbm_step_with_macroscopics");
+    *rho = h->rho_out; *u = (const float*)h->u_out;
+    return LBM_OK;
+}
+
+extern "C" int lbm_get_macroscopics(lbm_handle* h, float* rho, float* u) {
+    const float *dr, *du;
+    int rc = lbm_get_macroscopics_device(h, &dr, &du);
+    if (rc) return rc;
+    if (!rho || !u) return fail(LBM_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaMemcpyAsync(rho, dr, (size_t)h->nloc * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(u, du, (size_t)h->nloc * 8, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return LBM_OK;
+}
+
+extern "C" int lbm_total_mass(lbm_handle* h, double* out) {
+    if (!h || !out) return fail(LBM_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaMemsetAsync(h->mass_acc, 0, 8, h->stream));
+    Params p = make_params(h, h->timestep);
+    if (h->timestep & 1) mass_kernel<true><<<grid_of(h), BX, 0, h->stream>>>(p, h->mass_acc);
+    else mass_kernel<false><<<grid_of(h), BX, 0, h->stream>>>(p, h->mass_acc);
+    h->launches++;
+    CU(cudaMemcpyAsync(out, h->mass_acc, 8, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return LBM_OK;
+}
+
+extern "C" int lbm_moment_avg(lbm_handle* h, float out[3]) {
+    if (!h || !out) return fail(LBM_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaMemcpyAsync(out, h->avg, 12, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return LBM_OK;
+}
+
+extern "C" int lbm_get_moment_sums(lbm_handle* h, double s[3]) {
+    if (!h || !s) return fail(LBM_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaMemcpyAsync(s, h->sums, 24, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return LBM_OK;
+}
+
+extern "C" int lbm_set_moment_sums(lbm_handle* h, const double s[3]) {
+    if (!h || !s) return fail(LBM_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaMemcpyAsync(h->sums, s, 24, cudaMemcpyHostToDevice, h->stream));
+    sums_to_avg_kernel<<<1, 32, 0, h->stream>>>(h->sums, h->avg, 1.0 / ((double)h->cfg.nx * (double)h->cfg.ny));
+    h->launches++;
+    h->avg_for_ts = h->timestep + 1;
+    return LBM_OK;
+}
+
+extern "C" int lbm_info(lbm_handle* h, lbm_info_t* o) {
+    if (!h || !o) return fail(LBM_ERR_INVALID, "NULL argument");
+    memset(o, 0, sizeof(*o));
+    o->nx = h->cfg.nx; o->ny = h->cfg.ny; o->y0 = h->y0; o->ny_local = h->nyl; o->rank = h->cfg.rank; o->world = h->cfg.world;
+    o->timestep = h->timestep; o->num_markers = h->np; o->num_ibm_nodes = h->ibm_count; o->num_neighbour_bc_nodes = h->nbr_count;
+    o->device_bytes = h->bytes; o->bytes_per_cell = (double)h->bytes / (double)h->nloc; o->kernel_launches = h->launches;
+    return LBM_OK;
+}
+
+// ------------------------------------------------------------------ slab halos
+// Odd steps read A[opp q] of the neighbour's edge row for the three q that enter this slab and write A[q]
+// of it for the three q that leave.  side 0 (lower y): entering q = 2,5,6 -> slots 4,7,8; side 1: slots 2,5,6.
+static const int kSlots[2][3] = {{4, 7, 8}, {2, 5, 6}};
+
+extern "C" int lbm_next_step_needs_halo(lbm_handle* h) {
+    if (!h) return 0;
+    return (h->cfg.world > 1 && ((h->timestep + 1) & 1)) ? 1 : 0;
+}
+
+static bool has_neighbour(const lbm_handle* h, int side) {
+    if (h->cfg.world == 1) return false;
+    if (h->cfg.periodic_y) return true;
+    return side == 0 ? h->cfg.rank > 0 : h->cfg.rank < h->cfg.world - 1;
+}
+
+// row index (in plane rows, ghost offset included) of: own edge row / ghost row on a side
+static int own_edge_row(const lbm_handle* h, int side) { return side == 0 ? 1 : h->nyl; }
+static int ghost_row(const lbm_handle* h, int side) { return side == 0 ? 0 : h->nyl + 1; }
+
+static int copy_rows(lbm_handle* h, int row, const int slots[3], float* buf, bool to_buf) {
+    const size_t nx = h->cfg.nx;
+    for (int i = 0; i < 3; i++) {
+        float* src = h->pop + (size_t)slots[i] * h->plane + (size_t)row * nx;
+        if (to_buf) CU(cudaMemcpyAsync(buf + i * nx, src, nx * 4, cudaMemcpyDeviceToDevice, h->stream));
+        else CU(cudaMemcpyAsync(src, buf + i * nx, nx * 4, cudaMemcpyDeviceToDevice, h->stream));
+    }
+    return LBM_OK;
+}
+
+// pre: the OWNER of an edge row packs the slots its neighbour on `side` will read.
+// The neighbour above me (side 1) reads my top row's slots 4,7,8 (it is its "side 0" data) and vice versa.
+extern "C" int lbm_halo_pack_pre(lbm_handle* h, int side, float* buf) {
+    if (!h || !buf || side < 0 || side > 1) return fail(LBM_ERR_INVALID, "bad argument");
+    if (!has_neighbour(h, side)) return LBM_OK;
+    CU(cudaSetDevice(h->cfg.device));
+    return copy_rows(h, own_edge_row(h, side), kSlots[1 - side], buf, true);
+}
+extern "C" int lbm_halo_unpack_pre(lbm_handle* h, int side, const float* buf) {
+    if (!h || !buf || side < 0 || side > 1) return fail(LBM_ERR_INVALID, "bad argument");
+    if (!has_neighbour(h, side)) return LBM_OK;
+    CU(cudaSetDevice(h->cfg.device));
+    return copy_rows(h, ghost_row(h, side), kSlots[side], (float*)buf, false);
+}
+// post: what this slab wrote into its ghost row on `side` goes back into the neighbour's edge row.
+extern "C" int lbm_halo_pack_post(lbm_handle* h, int side, float* buf) {
+    if (!h || !buf || side < 0 || side > 1) return fail(LBM_ERR_INVALID, "bad argument");
+    if (!has_neighbour(h, side)) return LBM_OK;
+    CU(cudaSetDevice(h->cfg.device));
+    return copy_rows(h, ghost_row(h, side), kSlots[side], buf, true);
+}
+extern "C" int lbm_halo_unpack_post(lbm_handle* h, int side, const float* buf) {
+    if (!h || !buf || side < 0 || side > 1) return fail(LBM_ERR_INVALID, "bad argument");
+    if (!has_neighbour(h, side)) return LBM_OK;
+    CU(cudaSetDevice(h->cfg.device));
+    return copy_rows(h, own_edge_row(h, side), kSlots[1 - side], (float*)buf, false);
+}
+
+extern "C" int lbm_host_alloc(void** out, int64_t bytes) {
+    if (!out || bytes <= 0) return fail(LBM_ERR_INVALID, "bad argument");
+    CU(cudaHostAlloc(out, (size_t)bytes, cudaHostAllocDefault));
+    return LBM_OK;
+}
+extern "C" int lbm_host_free(void* p) {
+    if (p) CU(cudaFreeHost(p));
+    return LBM_OK;
+}

@@ -1,0 +1,103 @@
+"""y-slab decomposition of the D2Q9 domain over the GPUs of one box.
+
+One process per GPU (torchrun); slab g owns rows [y0, y0+ny_local).  The in-place AA pattern touches
+the neighbour slab only on odd steps: before such a step a rank needs, per face, the three
+populations of the neighbour's edge row that stream into it (3*nx floats), and after it the three
+populations it wrote for the neighbour travel back.  torch.distributed (NCCL over NVLink on the
+GPU box, gloo in the CPU tests) moves those rows; everything else is local.  The only other
+collective is the 3-double all-reduce of CM<2,OptimalAdapter>'s grid sums.
+
+The engine is passed in as an object with the halo/step methods of cuda_lbm_b200.solver.Engine so that
+the exchange schedule can be tested on CPU with a stand-in (tests/test_slab_gloo.py).
+"""
+import torch
+import torch.distributed as dist
+
+
+def neighbours(rank, world, periodic_y):
+    """(lower-y rank, upper-y rank) or None where the slab touches a non-periodic domain edge."""
+    if world == 1:
+        return None, None
+    lo = rank - 1 if rank > 0 else (world - 1 if periodic_y else None)
+    hi = rank + 1 if rank < world - 1 else (0 if periodic_y else None)
+    return lo, hi
+
+
+def slab_rows(ny, rank, world):
+    """Row range of a slab — same rule as lbm_create (engine.cu): the first ny % world slabs get one extra row."""
+    base, rem = divmod(ny, world)
+    n = base + (1 if rank < rem else 0)
+    y0 = rank * base + min(rank, rem)
+    return y0, n
+
+
+class SlabExchange:
+    """Halo exchange schedule for one rank.  `engine.halo(what, side, ptr)` packs / unpacks 3*nx floats."""
+
+    def __init__(self, engine, nx, periodic_y, device, rank=None, world=None, group=None):
+        self.e = engine
+        self.group = group
+        self.rank = dist.get_rank(group) if rank is None else rank
+        self.world = dist.get_world_size(group) if world is None else world
+        self.lo, self.hi = neighbours(self.rank, self.world, periodic_y)
+        self.send = [torch.zeros(3 * nx, dtype=torch.float32, device=device) for _ in range(2)]
+        self.recv = [torch.zeros(3 * nx, dtype=torch.float32, device=device) for _ in range(2)]
+        self.bytes_per_exchange = sum(3 * nx * 4 for p in (self.lo, self.hi) if p is not None)
+
+    def exchange(self, phase):
+        """phase 'pre': edge rows -> neighbours' ghost rows; 'post': ghost rows -> neighbours' edge rows."""
+        peers = (self.lo, self.hi)
+        for side in (0, 1):
+            if peers[side] is not None:
+                self.e.halo("pack_" + phase, side, self.send[side].data_ptr())
+        ops = []
+        # a message packed on my side s is consumed on the peer's side 1-s; when both faces touch the same peer
+        # (world == 2, periodic) messages match in posting order, hence receives are posted in reverse side order
+        for side in (0, 1):
+            if peers[side] is not None:
+                ops.append(dist.P2POp(dist.isend, self.send[side], peers[side], group=self.group))
+        for side in (1, 0):
+            if peers[side] is not None:
+                ops.append(dist.P2POp(dist.irecv, self.recv[side], peers[side], group=self.group))
+        if ops:
+            for r in dist.batch_isend_irecv(ops):
+                r.wait()
+        for side in (0, 1):
+            if peers[side] is not None:
+                self.e.halo("unpack_" + phase, side, self.recv[side].data_ptr())
+
+
+class SlabSolver:
+    """The solver loop of one rank: lbm_step one step at a time with halos in between."""
+
+    def __init__(self, engine, nx, periodic_y, device, optimal_adapter=False, adapter_exact=True, group=None):
+        self.e = engine
+        self.x = SlabExchange(engine, nx, periodic_y, device, group=group)
+        self.world = self.x.world
+        self.optimal, self.exact = optimal_adapter, adapter_exact
+        self.group = group
+        self._sums = torch.zeros(3, dtype=torch.float64, device=device)
+        self.collectives = 0
+
+    def _allreduce_sums(self):
+        s = torch.tensor(self.e.moment_sums(), dtype=torch.float64, device=self._sums.device)
+        dist.all_reduce(s, group=self.group)
+        self.e.set_moment_sums(s.cpu().tolist())
+        self.collectives += 1
+
+    def step(self, n=1, macroscopics=False):
+        if self.world == 1:
+            self.e.step(n, macroscopics=macroscopics)
+            return
+        for i in range(n):
+            need = self.e.next_step_needs_halo()
+            if need:
+                self.x.exchange("pre")
+            if self.optimal and self.exact:
+                self.e.adapter_prepass()
+                self._allreduce_sums()
+            self.e.step(1, macroscopics=macroscopics and i == n - 1)
+            if self.optimal and not self.exact:
+                self._allreduce_sums()
+            if need:
+                self.x.exchange("post")

@@ -1,0 +1,261 @@
+"""Host-side mirror of the reference's solver interface over the C ABI.
+
+`Engine`  — one handle of include/lbm_b200.h with numpy in/out.
+`LBM`     — the reference's `LBM<2>` (src/core/lbm.cuh:33-382) with the same method names and the
+            same driver protocol as src/main.cu:72-153: allocate(S), init(S), then per step
+            increase_ts / stream / swap_buffers / apply_boundaries / uncorrected_macroscopics /
+            reset_forces / ibm_step / correct_macroscopics / compute_equilibrium / collide, and
+            occasionally update_macroscopics / compute_error.  The nine per-kernel methods only
+            record the step; the fused kernel runs once per step when the step is closed.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi as capi
+from ._capi import LbmConfig, LbmInfo, check, lib
+
+
+def _fp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def default_S(collision, omega):
+    """Scenario::S in the row order the operator indexes it (reference scenario.cuh:47-57 for BGK/MRT,
+    lidDrivenCavityScenario.cuh:49-59 for CM)."""
+    om = np.float32(omega)
+    if collision >= capi.CM:
+        return np.array([0, 0, 0, 1, om, om, 1, 1, 1], np.float32)
+    return np.array([0, om, om, 0, om, 0, om, om, om], np.float32)
+
+
+class Engine:
+    def __init__(self, nx, ny, collision=capi.BGK, viscosity=1.0 / 6.0, S=None, periodic=(True, True), u_max=0.1,
+                 force=(0.0, 0.0), quirks=capi.QK_REFERENCE, adapter_mode=capi.ADAPTER_EXACT, device=0, rank=0, world=1):
+        L = lib()
+        cfg = LbmConfig()
+        check(L.lbm_default_config(C.byref(cfg)))
+        cfg.nx, cfg.ny = nx, ny
+        cfg.periodic_x, cfg.periodic_y = int(periodic[0]), int(periodic[1])
+        cfg.collision = collision
+        cfg.viscosity = float(np.float32(viscosity))
+        tau = np.float32(3) * np.float32(viscosity) + np.float32(0.5)
+        self.omega = np.float32(1.0) / tau
+        if S is None:
+            S = default_S(collision, self.omega)
+        for i, s in enumerate(np.asarray(S, np.float32)):
+            cfg.S[i] = float(s)
+        cfg.u_max = float(np.float32(u_max))
+        cfg.force_x, cfg.force_y = float(np.float32(force[0])), float(np.float32(force[1]))
+        cfg.quirks, cfg.adapter_mode = quirks, adapter_mode
+        cfg.device, cfg.rank, cfg.world = device, rank, world
+        self.cfg = cfg
+        self._h = C.c_void_p()
+        check(L.lbm_create(C.byref(cfg), C.byref(self._h)))
+        self.nx, self.ny = nx, ny
+        inf = self.info()
+        self.y0, self.ny_local = inf.y0, inf.ny_local
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            lib().lbm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def info(self):
+        o = LbmInfo()
+        check(lib().lbm_info(self._h, C.byref(o)))
+        return o
+
+    def set_stream(self, cuda_stream_ptr):
+        check(lib().lbm_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+
+    def set_flags(self, flags):
+        f = np.ascontiguousarray(flags, np.int32).reshape(-1)
+        if f.size != self.nx * self.ny:
+            raise ValueError("flags must cover the global grid")
+        check(lib().lbm_set_flags(self._h, f.ctypes.data_as(C.POINTER(C.c_int32))))
+
+    def set_body_force(self, fx, fy):
+        check(lib().lbm_set_body_force(self._h, float(np.float32(fx)), float(np.float32(fy))))
+
+    def set_force_field(self, force):
+        if force is None:
+            check(lib().lbm_set_force_field(self._h, None))
+            return
+        f = np.ascontiguousarray(force, np.float32).reshape(-1)
+        check(lib().lbm_set_force_field(self._h, _fp(f)))
+
+    def add_body(self, points):
+        p = np.ascontiguousarray(points, np.float32).reshape(-1)
+        check(lib().lbm_add_body(self._h, _fp(p), p.size // 2))
+
+    def init_fields(self, rho, u):
+        rho = np.ascontiguousarray(rho, np.float32).reshape(-1)
+        u = np.ascontiguousarray(u, np.float32).reshape(-1)
+        if rho.size != self.nx * self.ny or u.size != 2 * rho.size:
+            raise ValueError("rho/u must cover the global grid")
+        check(lib().lbm_init_fields(self._h, _fp(rho), _fp(u)))
+
+    def init_taylor_green(self, nu, u0):
+        check(lib().lbm_init_taylor_green(self._h, float(np.float32(nu)), float(np.float32(u0))))
+
+    def set_populations(self, f, f_back=None):
+        f = np.ascontiguousarray(f, np.float32).reshape(-1)
+        fb = None if f_back is None else np.ascontiguousarray(f_back, np.float32).reshape(-1)
+        check(lib().lbm_set_populations(self._h, _fp(f), None if fb is None else _fp(fb)))
+
+    def populations(self):
+        """Post-collision populations of this slab's rows, [ny_local, nx, 9]."""
+        f = np.zeros(self.nx * self.ny * 9, np.float32)
+        check(lib().lbm_get_populations(self._h, _fp(f)))
+        return f.reshape(self.ny, self.nx, 9)[self.y0:self.y0 + self.ny_local]
+
+    def step(self, n=1, macroscopics=False):
+        fn = lib().lbm_step_with_macroscopics if macroscopics else lib().lbm_step
+        check(fn(self._h, n))
+
+    def sync(self):
+        check(lib().lbm_sync(self._h))
+
+    def macroscopics(self):
+        rho = np.empty(self.nx * self.ny_local, np.float32)
+        u = np.empty(2 * self.nx * self.ny_local, np.float32)
+        check(lib().lbm_get_macroscopics(self._h, rho.ctypes.data_as(C.c_void_p), u.ctypes.data_as(C.c_void_p)))
+        return rho.reshape(self.ny_local, self.nx), u.reshape(self.ny_local, self.nx, 2)
+
+    def macroscopics_into(self, rho_ptr, u_ptr):
+        """D2H into caller-owned (ideally pinned) host memory given as integer addresses."""
+        check(lib().lbm_get_macroscopics(self._h, C.c_void_p(rho_ptr), C.c_void_p(u_ptr)))
+
+    def total_mass(self):
+        m = C.c_double()
+        check(lib().lbm_total_mass(self._h, C.byref(m)))
+        return m.value
+
+    def moment_avg(self):
+        a = np.empty(3, np.float32)
+        check(lib().lbm_moment_avg(self._h, _fp(a)))
+        return a
+
+    def moment_sums(self):
+        s = (C.c_double * 3)()
+        check(lib().lbm_get_moment_sums(self._h, s))
+        return np.array(list(s))
+
+    def set_moment_sums(self, sums):
+        s = (C.c_double * 3)(*[float(v) for v in sums])
+        check(lib().lbm_set_moment_sums(self._h, s))
+
+    def adapter_prepass(self):
+        check(lib().lbm_adapter_prepass(self._h))
+
+    # --- slab halos (device pointers as ints) ---
+    def next_step_needs_halo(self):
+        return bool(lib().lbm_next_step_needs_halo(self._h))
+
+    def halo(self, what, side, ptr):
+        fn = getattr(lib(), "lbm_halo_" + what)
+        check(fn(self._h, side, C.c_void_p(ptr)))
+
+
+class LBM:
+    """Drop-in for the reference's `LBM<2>` object (see module docstring).  `Scenario` objects follow
+    cuda_lbm_b200.scenarios.ScenarioTrait, the mirror of src/scenarios/scenario.cuh:22-78."""
+
+    def __init__(self, nx, ny, device=0, quirks=capi.QK_REFERENCE, adapter_mode=capi.ADAPTER_EXACT):
+        self.NX, self.NY = nx, ny
+        self.device, self.quirks, self.adapter_mode = device, quirks, adapter_mode
+        self.timestep = 0
+        self.update_ts = 0
+        self.h_rho = np.zeros(nx * ny, np.float32)
+        self.h_u = np.zeros(2 * nx * ny, np.float32)
+        self.engine = None
+        self._pending = False
+
+    # LBM::allocate<Scenario>()  lbm.cuh:92-125
+    def allocate(self, S):
+        self.engine = Engine(self.NX, self.NY, collision=S.collision, viscosity=S.viscosity, S=S.S, periodic=S.periodic,
+                             u_max=S.u_max, force=S.body_force(self.NX, self.NY), quirks=self.quirks,
+                             adapter_mode=self.adapter_mode, device=self.device)
+        S.IBM_bodies.clear()
+        S.add_bodies(self.NX, self.NY)
+        for body in S.IBM_bodies:
+            self.engine.add_body(body)
+
+    # LBM::init<Scenario>()  init.cuh:45-86
+    def init(self, S):
+        init = S.init(self.NX, self.NY)
+        rho, u = init()
+        boundary = S.boundary(self.NX, self.NY)
+        yy, xx = np.meshgrid(np.arange(self.NY), np.arange(self.NX), indexing="ij")
+        self.engine.set_flags(boundary(xx, yy))
+        self.engine.init_fields(rho, u)
+        self.timestep = 0
+        self._pending = False
+
+    def _close_step(self, macroscopics=False):
+        if self._pending:
+            self.engine.step(1, macroscopics=macroscopics)
+            self._pending = False
+
+    def increase_ts(self, S=None):
+        self._close_step()
+        self.timestep += 1
+        if S is not None:
+            S.update_ts(self.timestep)
+
+    # the reference's per-kernel host methods (lbm.cuh:345-377): recorded, executed fused
+    def stream(self): pass
+    def swap_buffers(self): pass
+    def apply_boundaries(self, S=None): pass
+    def uncorrected_macroscopics(self): pass
+    def reset_forces(self, S=None): pass
+    def ibm_step(self): pass
+    def correct_macroscopics(self): pass
+    def compute_equilibrium(self): pass
+
+    def collide(self, op=None):
+        self._pending = True
+
+    def run(self, nsteps, S=None):
+        """nsteps iterations of the main.cu loop body without the per-call overhead."""
+        self._close_step()
+        if nsteps > 0:
+            self.engine.step(nsteps - 1)
+            self.timestep += nsteps
+            self._pending = True
+            if S is not None:
+                S.update_ts(self.timestep)
+
+    # LBM::update_macroscopics()  lbm.cuh:148-154
+    def update_macroscopics(self):
+        if self._pending:
+            self._close_step(macroscopics=True)
+        rho, u = self.engine.macroscopics()
+        self.h_rho[:] = rho.reshape(-1)
+        self.h_u[:] = u.reshape(-1)
+        self.update_ts = self.timestep
+
+    def get_rho(self):
+        return self.h_rho
+
+    def get_u(self):
+        return self.h_u
+
+    # LBM::compute_error<Scenario>()  lbm.cuh:163-171
+    def compute_error(self, S):
+        if S.has_analytical_solution:
+            return S.compute_error(self)
+        print("Scenario does not provide verification/validation.")
+        return 0.0
+
+    def free(self):
+        if self.engine is not None:
+            self.engine.close()
+            self.engine = None
