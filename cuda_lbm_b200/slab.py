@@ -37,8 +37,11 @@ class SlabExchange:
     def __init__(self, engine, nx, periodic_y, device, rank=None, world=None, group=None):
         self.e = engine
         self.group = group
-        self.rank = dist.get_rank(group) if rank is None else rank
-        self.world = dist.get_world_size(group) if world is None else world
+        if rank is None or world is None:
+            on = dist.is_available() and dist.is_initialized()
+            rank = dist.get_rank(group) if on else 0
+            world = dist.get_world_size(group) if on else 1
+        self.rank, self.world = rank, world
         self.lo, self.hi = neighbours(self.rank, self.world, periodic_y)
         self.send = [torch.zeros(3 * nx, dtype=torch.float32, device=device) for _ in range(2)]
         self.recv = [torch.zeros(3 * nx, dtype=torch.float32, device=device) for _ in range(2)]
