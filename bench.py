@@ -163,7 +163,10 @@ def main():
     scale = nx / 128.0
     eng = L.Engine(nx, ny, collision=coll, viscosity=NU, periodic=(True, True), u_max=0.04, device=local, rank=rank, world=world,
                    adapter_mode=L.ADAPTER_LAGGED)
-    stream = torch.cuda.current_stream()
+    # one explicit stream for the engine's kernels, the NCCL halo traffic and the timing events
+    # (torch's legacy default stream has handle 0, which lbm_set_stream reads as "use the handle's own stream")
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     eng.set_stream(stream.cuda_stream)
     solver = SlabSolver(eng, nx, True, dev, optimal_adapter=(coll == L.CM_OPTIMAL), adapter_exact=False)
     nloc = eng.ny_local * nx

@@ -62,7 +62,12 @@ struct Params {
     const float* avg;       // 3 floats: grid means of rho, rho|u|, |Pi| (OptimalAdapter)
     float* partials;        // per-block partial sums (3 per block) or nullptr
     float* rho_out; float2* u_out;     // macroscopic output of this step (nullptr = none)
+    // segments: 128 consecutive cells of one row.  segmask[yl*nsx + sx] != 0 marks a "general" segment (boundary flags,
+    // IBM nodes, per-node force, non-periodic domain edge); the vectorised kernel skips those and the scalar kernel
+    // processes exactly the ones listed in gen_list.
+    const uint8_t* segmask; int nsx; const int* gen_list;
 };
+constexpr int SEG = 128;
 
 __device__ __forceinline__ long long rowoff(const Params& p, int yl) { return (long long)(yl + 1) * p.nx; }
 

@@ -56,8 +56,10 @@ struct lbm_handle {
     int* csr_row = nullptr; int* csr_k = nullptr; float* csr_w = nullptr;
     float* ibm_rho = nullptr; float2* ibm_uprev = nullptr; float2* ibm_lagF = nullptr; float2* ibm_force = nullptr;
     int np = 0, ibm_count = 0, ibm_ss = 4;
+    // general-path segments (kernels.cuh): mask per 128-cell segment + compact list, rebuilt lazily
+    uint8_t* segmask = nullptr; int* gen_list = nullptr; int gen_count = 0; int nsx = 0; bool segs_dirty = true;
     // adapter
-    float* partials = nullptr; long long n_partials = 0; double* sums = nullptr; float* avg = nullptr; int avg_for_ts = -1; int pre_for_ts = -1;
+    float* partials = nullptr; long long n_partials = 0; double* stage = nullptr; double* sums = nullptr; float* avg = nullptr; int avg_for_ts = -1; int pre_for_ts = -1;
     // macroscopics
     float* rho_out = nullptr; float2* u_out = nullptr; int macros_ts = -1;
     double* mass_acc = nullptr;
@@ -92,6 +94,7 @@ static Params make_params(lbm_handle* h, int t) {
     p.nbr_nodes = h->nbr_nodes; p.nbr_g = h->nbr_g; p.nbr_count = h->nbr_count;
     p.ibm_nodes = h->ibm_nodes; p.ibm_force = h->ibm_force; p.ibm_count = h->ibm_count;
     p.avg = h->avg; p.partials = nullptr; p.rho_out = nullptr; p.u_out = nullptr;
+    p.segmask = nullptr; p.nsx = h->nsx; p.gen_list = nullptr;
     return p;
 }
 
@@ -119,7 +122,7 @@ extern "C" int lbm_destroy(lbm_handle* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     void* ptrs[] = {h->pop, h->flags, h->force_plane, h->ring, h->nbr_nodes, h->nbr_src, h->nbr_g, h->d_pts, h->ibm_nodes,
                     h->sten_idx, h->sten_w, h->csr_row, h->csr_k, h->csr_w, h->ibm_rho, h->ibm_uprev, h->ibm_lagF, h->ibm_force,
-                    h->partials, h->sums, h->avg, h->rho_out, h->u_out, h->mass_acc};
+                    h->partials, h->stage, h->sums, h->avg, h->rho_out, h->u_out, h->mass_acc, h->segmask, h->gen_list};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
@@ -152,6 +155,7 @@ extern "C" int lbm_create(const lbm_config* cfg, lbm_handle** out) {
     h->nloc = (long long)h->nyl * cfg->nx;
     h->plane = (size_t)(h->nyl + 2) * cfg->nx;
     h->nplanes = (cfg->quirks & LBM_QK_D1_STALE_F0) ? 10 : 9;
+    h->nsx = (cfg->nx + SEG - 1) / SEG;
     cudaError_t e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete h; return fail(LBM_ERR_CUDA, cudaGetErrorString(e)); }
     h->stream = h->own_stream;
@@ -160,11 +164,7 @@ extern "C" int lbm_create(const lbm_config* cfg, lbm_handle** out) {
               dmalloc(h, &h->ring, (size_t)2 * h->perim * Q) == cudaSuccess &&
               dmalloc(h, &h->sums, 3) == cudaSuccess && dmalloc(h, &h->avg, 3) == cudaSuccess &&
               dmalloc(h, &h->mass_acc, 1) == cudaSuccess;
-    if (ok && cfg->collision == LBM_CM_OPTIMAL) {
-        dim3 g = grid_of(h);
-        h->n_partials = (long long)g.x * g.y;
-        ok = dmalloc(h, &h->partials, (size_t)3 * h->n_partials) == cudaSuccess;
-    }
+    if (ok && cfg->collision == LBM_CM_OPTIMAL) ok = dmalloc(h, &h->stage, (size_t)3 * RED_BLOCKS) == cudaSuccess;
     if (!ok) { std::string m = cudaGetErrorString(cudaGetLastError()); lbm_destroy(h); return fail(LBM_ERR_CUDA, "device allocation failed: " + m); }
     cudaMemsetAsync(h->pop, 0, h->plane * h->nplanes * sizeof(float), h->stream);
     cudaMemsetAsync(h->ring, 0, (size_t)2 * h->perim * Q * sizeof(float), h->stream);
@@ -245,6 +245,7 @@ extern "C" int lbm_set_flags(lbm_handle* h, const int32_t* flags) {
         CU(cudaMemcpy(h->nbr_nodes, a.data(), a.size() * 8, cudaMemcpyHostToDevice));
         CU(cudaMemcpy(h->nbr_src, b.data(), b.size() * 8, cudaMemcpyHostToDevice));
     }
+    h->segs_dirty = true;
     if (h->np > 0) return rebuild_ibm(h);       // re-mark the IBM bit
     return LBM_OK;
 }
@@ -258,6 +259,7 @@ extern "C" int lbm_set_body_force(lbm_handle* h, float fx, float fy) {
 extern "C" int lbm_set_force_field(lbm_handle* h, const float* force_aos) {
     if (!h) return fail(LBM_ERR_INVALID, "NULL handle");
     CU(cudaSetDevice(h->cfg.device));
+    h->segs_dirty = true;
     if (!force_aos) { if (h->force_plane) { cudaFree(h->force_plane); h->force_plane = nullptr; } return LBM_OK; }
     if (!h->force_plane) CU(dmalloc(h, &h->force_plane, (size_t)h->nloc));
     CU(cudaMemcpy(h->force_plane, force_aos + (size_t)2 * h->y0 * h->cfg.nx, (size_t)h->nloc * sizeof(float2), cudaMemcpyHostToDevice));
@@ -283,6 +285,7 @@ struct gather_idx { const int* idx; const int* ord; int* out; __device__ void op
 
 static int rebuild_ibm(lbm_handle* h) {
     CU(cudaSetDevice(h->cfg.device));
+    h->segs_dirty = true;
     if (h->cfg.world != 1) return fail(LBM_ERR_INVALID, "immersed bodies are supported on a single slab only (SURVEY.md 8e: cross-face stencils deferred)");
     auto pol = thrust::cuda::par.on(h->stream);
     if (h->ibm_nodes && h->flags && h->ibm_count) {
@@ -447,20 +450,70 @@ extern "C" int lbm_get_populations(lbm_handle* h, float* f) {
 }
 
 // ------------------------------------------------------------------ the time step
+static bool is_general(const lbm_handle* h) {
+    return h->flags != nullptr || h->force_plane != nullptr || !h->cfg.periodic_x || !h->cfg.periodic_y;
+}
+static bool use_vec(const lbm_handle* h) { return (h->cfg.nx % 4) == 0; }
+static dim3 vec_grid(const lbm_handle* h, int& threads) {
+    const int nv = h->cfg.nx / 4;
+    threads = std::min(BX, ((nv + 31) / 32) * 32);
+    return dim3((nv + threads - 1) / threads, h->nyl);
+}
+
+struct is_set_u8 { __host__ __device__ bool operator()(uint8_t v) const { return v != 0; } };
+
+// (re)build the general-segment mask and list after flags / bodies / force plane changed
+static int ensure_segments(lbm_handle* h) {
+    if (!h->segs_dirty) return LBM_OK;
+    const long long nseg = (long long)h->nsx * h->nyl;
+    if (!h->segmask) { CU(dmalloc(h, &h->segmask, (size_t)nseg)); CU(dmalloc(h, &h->gen_list, (size_t)nseg)); }
+    Params p = make_params(h, 0);
+    build_segmask_kernel<<<(unsigned)((nseg + 255) / 256), 256, 0, h->stream>>>(p, h->segmask);
+    h->launches++;
+    auto pol = thrust::cuda::par.on(h->stream);
+    thrust::device_ptr<uint8_t> mp(h->segmask);
+    thrust::device_ptr<int> lp(h->gen_list);
+    auto end = thrust::copy_if(pol, thrust::counting_iterator<int>(0), thrust::counting_iterator<int>((int)nseg), mp, lp, is_set_u8());
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    h->gen_count = (int)(end - lp);
+    h->segs_dirty = false;
+    return LBM_OK;
+}
+
+static int ensure_partials(lbm_handle* h, long long n) {
+    if (n <= h->n_partials) return LBM_OK;
+    if (h->partials) { CU(cudaStreamSynchronize(h->stream)); cudaFree(h->partials); h->bytes -= 12 * h->n_partials; h->partials = nullptr; }
+    CU(dmalloc(h, &h->partials, (size_t)3 * n));
+    h->n_partials = n;
+    return LBM_OK;
+}
+
+static void reduce_partials(lbm_handle* h, long long n) {
+    const double inv_n = 1.0 / ((double)h->cfg.nx * (double)h->cfg.ny);
+    const int nb = (int)std::min<long long>(RED_BLOCKS, (n + 255) / 256);
+    reduce_stage1_kernel<<<nb, 256, 0, h->stream>>>(h->partials, n, h->stage);
+    reduce_stage2_kernel<<<1, 256, 0, h->stream>>>(h->stage, nb, h->sums, h->avg, inv_n, h->cfg.world == 1);
+    h->launches += 2;
+}
+
 template <int COLL, bool ODD>
-static void launch_step(lbm_handle* h, const Params& p, bool general) {
-    if (general) step_kernel<COLL, ODD, true><<<grid_of(h), BX, 0, h->stream>>>(p);
-    else step_kernel<COLL, ODD, false><<<grid_of(h), BX, 0, h->stream>>>(p);
+static void launch_scalar(lbm_handle* h, const Params& p, bool general, dim3 grid) {
+    if (general) step_kernel<COLL, ODD, true><<<grid, BX, 0, h->stream>>>(p);
+    else step_kernel<COLL, ODD, false><<<grid, BX, 0, h->stream>>>(p);
 }
-template <bool ODD>
-static void launch_step_coll(lbm_handle* h, const Params& p, bool general) {
-    switch (h->cfg.collision) {
-    case LBM_BGK: launch_step<C_BGK, ODD>(h, p, general); break;
-    case LBM_MRT: launch_step<C_MRT, ODD>(h, p, general); break;
-    case LBM_CM: launch_step<C_CM, ODD>(h, p, general); break;
-    default: launch_step<C_CMOPT, ODD>(h, p, general); break;
+template <int COLL, bool ODD>
+static void launch_vec(lbm_handle* h, const Params& p) {
+    int threads; dim3 g = vec_grid(h, threads);
+    step_vec_kernel<COLL, ODD><<<g, threads, 0, h->stream>>>(p);
+}
+#define DISPATCH_COLL(ODDV, CALL)                                                     \
+    switch (h->cfg.collision) {                                                      \
+    case LBM_BGK: { constexpr int COLL = C_BGK; constexpr bool ODD = ODDV; CALL; } break;   \
+    case LBM_MRT: { constexpr int COLL = C_MRT; constexpr bool ODD = ODDV; CALL; } break;   \
+    case LBM_CM: { constexpr int COLL = C_CM; constexpr bool ODD = ODDV; CALL; } break;     \
+    default: { constexpr int COLL = C_CMOPT; constexpr bool ODD = ODDV; CALL; } break;      \
     }
-}
 
 // nbr gather + IBM (+ moments pre-pass) for step t; idempotent per timestep
 static int pre_passes(lbm_handle* h, int t, bool want_moments) {
@@ -481,11 +534,13 @@ static int pre_passes(lbm_handle* h, int t, bool want_moments) {
         h->pre_for_ts = t;
     }
     if (want_moments) {
-        const double inv_n = 1.0 / ((double)h->cfg.nx * (double)h->cfg.ny);
+        dim3 g = grid_of(h);
+        const long long nb = (long long)g.x * g.y;
+        int rc = ensure_partials(h, nb); if (rc) return rc;
         Params pm = p; pm.partials = h->partials;
-        if (odd) moments_kernel<true><<<grid_of(h), BX, 0, h->stream>>>(pm); else moments_kernel<false><<<grid_of(h), BX, 0, h->stream>>>(pm);
-        reduce_partials_kernel<<<1, 256, 0, h->stream>>>(h->partials, h->n_partials, h->sums, h->avg, inv_n, h->cfg.world == 1);
-        h->launches += 2;
+        if (odd) moments_kernel<true><<<g, BX, 0, h->stream>>>(pm); else moments_kernel<false><<<g, BX, 0, h->stream>>>(pm);
+        h->launches++;
+        reduce_partials(h, nb);
         if (h->cfg.world == 1) h->avg_for_ts = t;
     }
     return LBM_OK;
@@ -494,7 +549,7 @@ static int pre_passes(lbm_handle* h, int t, bool want_moments) {
 static int one_step(lbm_handle* h, bool want_macros) {
     const int t = h->timestep + 1;
     const bool odd = (t & 1) != 0;
-    const bool general = h->flags != nullptr || h->force_plane != nullptr || !h->cfg.periodic_x || !h->cfg.periodic_y;
+    const bool general = is_general(h);
     const bool opt = h->cfg.collision == LBM_CM_OPTIMAL;
     const bool need_moments = opt && h->avg_for_ts != t;
     if (need_moments && h->cfg.world > 1)
@@ -502,14 +557,33 @@ static int one_step(lbm_handle* h, bool want_macros) {
     int rc = pre_passes(h, t, need_moments); if (rc) return rc;
     Params p = make_params(h, t);
     const bool lagged = opt && h->cfg.adapter_mode == LBM_ADAPTER_LAGGED;
-    if (lagged) p.partials = h->partials;
     if (want_macros) { rc = ensure_macros(h); if (rc) return rc; p.rho_out = h->rho_out; p.u_out = h->u_out; }
-    if (odd) launch_step_coll<true>(h, p, general); else launch_step_coll<false>(h, p, general);
-    h->launches++;
-    if (lagged) {
-        const double inv_n = 1.0 / ((double)h->cfg.nx * (double)h->cfg.ny);
-        reduce_partials_kernel<<<1, 256, 0, h->stream>>>(h->partials, h->n_partials, h->sums, h->avg, inv_n, h->cfg.world == 1);
+    long long nparts = 0;
+    if (!use_vec(h)) {
+        // nx not a multiple of 4: the scalar kernel covers the whole slab
+        dim3 g = grid_of(h);
+        if (lagged) { nparts = (long long)g.x * g.y; rc = ensure_partials(h, nparts); if (rc) return rc; p.partials = h->partials; }
+        if (odd) { DISPATCH_COLL(true, (launch_scalar<COLL, ODD>(h, p, general, g))) } else { DISPATCH_COLL(false, (launch_scalar<COLL, ODD>(h, p, general, g))) }
         h->launches++;
+    } else {
+        if (general) { rc = ensure_segments(h); if (rc) return rc; }
+        const int ngen = general ? h->gen_count : 0;
+        int threads; dim3 gv = vec_grid(h, threads);
+        const long long nvb = (long long)gv.x * gv.y;
+        if (lagged) { nparts = nvb + ngen; rc = ensure_partials(h, nparts); if (rc) return rc; p.partials = h->partials; }
+        if (general) p.segmask = h->segmask;
+        if (odd) { DISPATCH_COLL(true, (launch_vec<COLL, ODD>(h, p))) } else { DISPATCH_COLL(false, (launch_vec<COLL, ODD>(h, p))) }
+        h->launches++;
+        if (ngen > 0) {
+            Params pg = p; pg.segmask = nullptr; pg.gen_list = h->gen_list;
+            if (lagged) pg.partials = h->partials + 3 * nvb;
+            dim3 g(ngen, 1);
+            if (odd) { DISPATCH_COLL(true, (launch_scalar<COLL, ODD>(h, pg, true, g))) } else { DISPATCH_COLL(false, (launch_scalar<COLL, ODD>(h, pg, true, g))) }
+            h->launches++;
+        }
+    }
+    if (lagged) {
+        reduce_partials(h, nparts);
         if (h->cfg.world == 1) h->avg_for_ts = t + 1;
     }
     h->timestep = t;

@@ -57,11 +57,21 @@ __device__ __forceinline__ void block_partials(float a, float b, float c, float*
     }
 }
 
-// The fused step: one launch = one reference time step (src/main.cu:96-114) for every node of the slab.
+// The fused step: one launch = one reference time step (src/main.cu:96-114) for every node it covers.
+// Scalar form, one cell per thread.  Two launch shapes: the whole slab (grid = segments x rows; used when nx is not a
+// multiple of 4) or only the "general" segments listed in p.gen_list (grid.x = number of listed segments), the
+// vectorised kernel below covering everything else.
 template <int COLL, bool ODD, bool GENERAL>
 __global__ void __launch_bounds__(BX) step_kernel(const Params p) {
-    const int x = blockIdx.x * BX + threadIdx.x;
-    const int yl = blockIdx.y;
+    int x, yl;
+    if (p.gen_list) {
+        const int seg = p.gen_list[blockIdx.x];
+        yl = seg / p.nsx;
+        x = (seg - yl * p.nsx) * SEG + threadIdx.x;
+    } else {
+        x = blockIdx.x * BX + threadIdx.x;
+        yl = blockIdx.y;
+    }
     float s0 = 0.f, s1 = 0.f, s2 = 0.f;
     if (x < p.nx) {
         NodeState s;
@@ -81,6 +91,139 @@ __global__ void __launch_bounds__(BX) step_kernel(const Params p) {
     if (COLL == C_CMOPT && p.partials) block_partials(s0, s1, s2, p.partials + 3 * ((long long)blockIdx.y * gridDim.x + blockIdx.x));
 }
 
+// ------------------------------------------------------------------ vectorised fast path
+// Four consecutive cells of one row per thread, 128-bit loads and stores on every slot plane.  Covers the cells that
+// need nothing but stream + collide (FLUID, uniform body force, away from non-periodic domain edges): everything of a
+// periodic Taylor-Green box, all but O(perimeter + bodies) segments elsewhere.
+//   even step: every slot is read and written at the cell's own address -> aligned float4.
+//   odd step : slot planes with c_x != 0 are shifted by one cell.  Each thread still issues one ALIGNED float4 access per
+//              plane and the one element that crosses the 16-byte boundary moves between neighbouring lanes with a
+//              warp shuffle; only the first / last lane of a warp (or of a row) touch the odd element with a scalar access.
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float a, float b, float c, float d) { *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d); }
+
+// values of plane row `r` at x0-1 .. x0+2 (source of a population moving in +x)
+__device__ __forceinline__ void load_from_left(const float* r, int x0, int xl, bool hasL, float o[4]) {
+    const float4 v = ld4(r + x0);
+    float l = __shfl_up_sync(FULL, v.w, 1);
+    if (!hasL) l = r[xl];
+    o[0] = l; o[1] = v.x; o[2] = v.y; o[3] = v.z;
+}
+// values at x0+1 .. x0+4 (source of a population moving in -x)
+__device__ __forceinline__ void load_from_right(const float* r, int x0, int xr, bool hasR, float o[4]) {
+    const float4 v = ld4(r + x0);
+    float rr = __shfl_down_sync(FULL, v.x, 1);
+    if (!hasR) rr = r[xr];
+    o[0] = v.y; o[1] = v.z; o[2] = v.w; o[3] = rr;
+}
+// f[0..3] of cells x0..x0+3 go to x0+1 .. x0+4
+__device__ __forceinline__ void store_to_right(float* r, int x0, int xr, bool hasL, bool hasR, bool act, const float f[4]) {
+    const float l = __shfl_up_sync(FULL, f[3], 1);
+    if (!act) return;
+    if (hasL) st4(r + x0, l, f[0], f[1], f[2]);
+    else { r[x0 + 1] = f[0]; r[x0 + 2] = f[1]; r[x0 + 3] = f[2]; }
+    if (!hasR) r[xr] = f[3];
+}
+// f[0..3] go to x0-1 .. x0+2
+__device__ __forceinline__ void store_to_left(float* r, int x0, int xl, bool hasL, bool hasR, bool act, const float f[4]) {
+    const float rr = __shfl_down_sync(FULL, f[0], 1);
+    if (!act) return;
+    if (hasR) st4(r + x0, f[1], f[2], f[3], rr);
+    else { r[x0] = f[1]; r[x0 + 1] = f[2]; r[x0 + 2] = f[3]; }
+    if (!hasL) r[xl] = f[0];
+}
+
+template <int COLL, bool ODD>
+__global__ void __launch_bounds__(BX) step_vec_kernel(const Params p) {
+    const int nv = p.nx >> 2;
+    const int xv_raw = blockIdx.x * blockDim.x + threadIdx.x;
+    const int yl = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    bool act = xv_raw < nv;
+    const int xv = act ? xv_raw : nv - 1;             // idle lanes of the last warp shadow a valid cell (loads only)
+    bool warp_on = (xv_raw & ~31) < nv;               // warp-uniform: one warp = one 128-cell segment
+    if (warp_on && p.segmask) warp_on = p.segmask[(long long)yl * p.nsx + (xv_raw >> 5)] == 0;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    if (warp_on) {
+        const int x0 = xv << 2;
+        const long long r0 = rowoff(p, yl);
+        const int gen = p.t & 1;
+        float g[4][Q];
+        // neighbours inside the warp exchange the boundary element; a row starts at lane 0 (blockDim.x % 32 == 0)
+        const bool hasL = lane > 0, hasR = lane < 31 && xv_raw < nv - 1;
+        int xl = x0 - 1, xr = x0 + 4;
+        if (xl < 0) xl += p.nx;
+        if (xr >= p.nx) xr -= p.nx;
+        long long rm = 0, rp = 0;
+        {
+            float4 v = ld4(p.A0[gen] + r0 + x0);
+            g[0][0] = v.x; g[1][0] = v.y; g[2][0] = v.z; g[3][0] = v.w;
+        }
+        if (!ODD) {
+#pragma unroll
+            for (int q = 1; q < Q; q++) {
+                float4 v = ld4(p.A[q] + r0 + x0);
+                g[0][q] = v.x; g[1][q] = v.y; g[2][q] = v.z; g[3][q] = v.w;
+            }
+        } else {
+            int ym = yl - 1, yp = yl + 1;
+            if (p.wrap_y) { if (ym < 0) ym += p.nyl; if (yp >= p.nyl) yp -= p.nyl; }
+            rm = rowoff(p, ym); rp = rowoff(p, yp);
+#pragma unroll
+            for (int q = 1; q < Q; q++) {
+                // g_q(x) = A[opp q][x - c_q]: source row y - c_y, source column x - c_x
+                const float* r = p.A[opp(q)] + (cy(q) > 0 ? rm : (cy(q) < 0 ? rp : r0));
+                float o[4];
+                if (cx(q) > 0) load_from_left(r, x0, xl, hasL, o);
+                else if (cx(q) < 0) load_from_right(r, x0, xr, hasR, o);
+                else { float4 v = ld4(r + x0); o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
+                g[0][q] = o[0]; g[1][q] = o[1]; g[2][q] = o[2]; g[3][q] = o[3];
+            }
+        }
+        float rho4[4], ux4[4], uy4[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            Moments m = moments(g[c]);
+            const float Fx = p.fx, Fy = p.fy;
+            const float h = 0.5f / m.rho;
+            const float ux = m.ux + Fx * h, uy = m.uy + Fy * h;
+            rho4[c] = m.rho; ux4[c] = ux; uy4[c] = uy;
+            if (COLL == C_CMOPT && act) { s0 += m.rho; s1 += m.rho * sqrtf(ux * ux + uy * uy); s2 += pi_norm(m); }
+            if (COLL == C_BGK) collide_bgk(p, g[c], m.rho, ux, uy, Fx, Fy);
+            else if (COLL == C_MRT) collide_mrt(p, g[c], m.rho, ux, uy, Fx, Fy);
+            else if (COLL == C_CM) collide_cm<false>(p, g[c], ux, uy, Fx, Fy);
+            else collide_cm<true>(p, g[c], ux, uy, Fx, Fy);
+        }
+        if (p.rho_out && act) {
+            const long long ln = (long long)yl * p.nx + x0;
+            st4(p.rho_out + ln, rho4[0], rho4[1], rho4[2], rho4[3]);
+            float* uo = reinterpret_cast<float*>(p.u_out + ln);
+            st4(uo, ux4[0], uy4[0], ux4[1], uy4[1]);
+            st4(uo + 4, ux4[2], uy4[2], ux4[3], uy4[3]);
+        }
+        if (act) st4(p.A0[gen] + r0 + x0, g[0][0], g[1][0], g[2][0], g[3][0]);
+        if (!ODD) {
+            if (act) {
+#pragma unroll
+                for (int q = 1; q < Q; q++) st4(p.A[opp(q)] + r0 + x0, g[0][q], g[1][q], g[2][q], g[3][q]);
+            }
+        } else {
+#pragma unroll
+            for (int q = 1; q < Q; q++) {
+                // f*_q(x) -> A[q][x + c_q]: destination row y + c_y, destination column x + c_x
+                float* r = p.A[q] + (cy(q) > 0 ? rp : (cy(q) < 0 ? rm : r0));
+                const float f[4] = {g[0][q], g[1][q], g[2][q], g[3][q]};
+                if (cx(q) > 0) store_to_right(r, x0, xr, hasL, hasR, act, f);
+                else if (cx(q) < 0) store_to_left(r, x0, xl, hasL, hasR, act, f);
+                else if (act) st4(r + x0, f[0], f[1], f[2], f[3]);
+            }
+        }
+    }
+    if (COLL == C_CMOPT && p.partials) block_partials(s0, s1, s2, p.partials + 3 * ((long long)blockIdx.y * gridDim.x + blockIdx.x));
+}
+
 // moments pre-pass for LBM_ADAPTER_EXACT: the grid sums of the CURRENT post-stream state, before any cell collides
 template <bool ODD>
 __global__ void __launch_bounds__(BX) moments_kernel(const Params p) {
@@ -95,20 +238,33 @@ __global__ void __launch_bounds__(BX) moments_kernel(const Params p) {
     block_partials(s0, s1, s2, p.partials + 3 * ((long long)blockIdx.y * gridDim.x + blockIdx.x));
 }
 
-// deterministic final reduction of the block partials: sums[3] (fp64) and avg[3] = sums / (NX*NY)
-__global__ void reduce_partials_kernel(const float* partials, long long nblocks, double* sums, float* avg, double inv_n, int write_avg) {
+// deterministic two-level reduction of the block partials: stage 1 (many blocks) folds the fp32 partials into
+// at most RED_BLOCKS fp64 triples, stage 2 (one block) produces sums[3] and avg[3] = sums / (NX*NY)
+constexpr int RED_BLOCKS = 592;     // 4 per SM
+template <typename T>
+__device__ __forceinline__ void block_sum3(const T* in, long long n, long long start, long long stride, double out[3]) {
     __shared__ double sm[3][256];
     double a = 0.0, b = 0.0, c = 0.0;
-    for (long long i = threadIdx.x; i < nblocks; i += 256) { a += partials[3 * i]; b += partials[3 * i + 1]; c += partials[3 * i + 2]; }
+    for (long long i = start; i < n; i += stride) { a += (double)in[3 * i]; b += (double)in[3 * i + 1]; c += (double)in[3 * i + 2]; }
     sm[0][threadIdx.x] = a; sm[1][threadIdx.x] = b; sm[2][threadIdx.x] = c;
     __syncthreads();
     for (int s = 128; s > 0; s >>= 1) {
         if ((int)threadIdx.x < s) { sm[0][threadIdx.x] += sm[0][threadIdx.x + s]; sm[1][threadIdx.x] += sm[1][threadIdx.x + s]; sm[2][threadIdx.x] += sm[2][threadIdx.x + s]; }
         __syncthreads();
     }
+    out[0] = sm[0][0]; out[1] = sm[1][0]; out[2] = sm[2][0];
+}
+__global__ void __launch_bounds__(256) reduce_stage1_kernel(const float* partials, long long nblocks, double* stage) {
+    double o[3];
+    block_sum3(partials, nblocks, (long long)blockIdx.x * 256 + threadIdx.x, (long long)gridDim.x * 256, o);
+    if (threadIdx.x < 3) stage[3 * blockIdx.x + threadIdx.x] = o[threadIdx.x];
+}
+__global__ void __launch_bounds__(256) reduce_stage2_kernel(const double* stage, int n, double* sums, float* avg, double inv_n, int write_avg) {
+    double o[3];
+    block_sum3(stage, n, threadIdx.x, 256, o);
     if (threadIdx.x < 3) {
-        sums[threadIdx.x] = sm[threadIdx.x][0];
-        if (write_avg) avg[threadIdx.x] = (float)(sm[threadIdx.x][0] * inv_n);
+        sums[threadIdx.x] = o[threadIdx.x];
+        if (write_avg) avg[threadIdx.x] = (float)(o[threadIdx.x] * inv_n);
     }
 }
 __global__ void sums_to_avg_kernel(const double* sums, float* avg, double inv_n) {
@@ -127,6 +283,22 @@ __global__ void nbr_gather_kernel(const Params p, const long long* nbr_src, floa
     pull<ODD>(p, x, yg - p.y0, g);
 #pragma unroll
     for (int q = 0; q < Q; q++) nbr_g[(long long)k * Q + q] = g[q];
+}
+
+// one thread per segment: does any of its cells need the general path?
+__global__ void build_segmask_kernel(const Params p, uint8_t* mask) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)p.nsx * p.nyl) return;
+    const int yl = (int)(i / p.nsx), sx = (int)(i - (long long)yl * p.nsx), yg = p.y0 + yl;
+    bool gen = p.force_plane != nullptr;
+    if (!p.py && (yg == 0 || yg == p.ny - 1)) gen = true;
+    if (!p.px && (sx == 0 || sx == p.nsx - 1)) gen = true;
+    if (!gen && p.flags) {
+        const int x1 = min(p.nx, (sx + 1) * SEG);
+        const uint8_t* f = p.flags + (long long)yl * p.nx;
+        for (int x = sx * SEG; x < x1; x++) if (f[x]) { gen = true; break; }
+    }
+    mask[i] = gen ? 1 : 0;
 }
 
 // ------------------------------------------------------------------ IBM

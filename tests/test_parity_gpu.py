@@ -87,3 +87,108 @@ def test_lagged_adapter_close_to_exact():
         outs.append(e.macroscopics())
         e.close()
     assert rel_l2(outs[1][1], outs[0][1]) < 5e-3
+
+
+# ---------------------------------------------------------------- vectorised path / segment logic at awkward sizes
+def _tg_case(nx, ny, coll):
+    return cases.Case(f"tg_{nx}x{ny}_{coll}", nx, ny, coll, 1.0 / 6.0, (True, True), 0.04, "tg", scale=max(1.0, nx / 128.0))
+
+
+@pytest.mark.parametrize("nx,ny", [(200, 12), (516, 9), (1024, 8), (4, 5), (132, 7)])
+@pytest.mark.parametrize("coll", [cases.BGK, cases.MRT, cases.CM, cases.CM_OPT])
+def test_vector_path_sizes_periodic(nx, ny, coll):
+    """Rows that end inside a warp (nx/4 not a multiple of 32), several warps per row, single-vector rows."""
+    case = _tg_case(nx, ny, coll)
+    case.u_max = np.float32(0.04)
+    for n, df, dr, du, fin in _run_pair(case, [1, 2, 3, 4, 9]):
+        assert fin and df <= TOL_F * max(1, n) ** 0.5 and dr <= TOL_RHO * max(1, n) ** 0.5, (nx, ny, coll, n, df, dr)
+
+
+@pytest.mark.parametrize("kind,nx,ny,periodic", [("pois", 264, 20, (True, False)), ("lid", 260, 36, (False, False)),
+                                                 ("cyl_ibm", 384, 64, (False, False)), ("cyl_flag", 260, 64, (False, False))])
+@pytest.mark.parametrize("coll", [cases.BGK, cases.MRT, cases.CM_OPT])
+def test_mixed_vector_and_general_segments(kind, nx, ny, periodic, coll):
+    """Grids where most segments take the vectorised kernel and edge / body segments take the scalar one."""
+    nu = 1.0 / 6.0 if kind == "pois" else (0.03 if kind == "lid" else float(cases._cyl_nu(ny)))
+    um = {"pois": 0.05, "lid": 0.1}.get(kind, 0.05)
+    force = cases._pois_force(ny) if kind == "pois" else (0.0, 0.0)
+    case = cases.Case(f"{kind}_{nx}x{ny}", nx, ny, coll, nu, periodic, um, kind, force=force, np_markers=24)
+    for n, df, dr, du, fin in _run_pair(case, [1, 2, 3, 4, 11]):
+        assert fin and df <= TOL_F * max(1, n) ** 0.5 and dr <= TOL_RHO * max(1, n) ** 0.5, (kind, coll, n, df, dr)
+
+
+# ---------------------------------------------------------------- y-slabs on one GPU: two/three handles + the halo API
+def _run_slabs(case, world, nsteps, adapter_mode=0):
+    """world handles on cuda:0 stepping in lock-step; halos moved through plain device buffers (what NCCL does in slab.py)."""
+    import torch
+    rho0, u0 = case.init_fields()
+    engs = [make_engine(case, adapter_mode=adapter_mode, rank=r, world=world) for r in range(world)]
+    for e in engs:
+        e.init_fields(rho0, u0)
+    nx = case.nx
+    bufs = {(r, s): torch.zeros(3 * nx, dtype=torch.float32, device="cuda") for r in range(world) for s in (0, 1)}
+    py = case.periodic[1]
+
+    def peer(r, side):
+        q = r - 1 if side == 0 else r + 1
+        if 0 <= q < world:
+            return q
+        return (q % world) if py else None
+
+    def exchange(phase):
+        for r, e in enumerate(engs):
+            for side in (0, 1):
+                if peer(r, side) is not None:
+                    e.halo("pack_" + phase, side, bufs[(r, side)].data_ptr())
+        for e in engs:
+            e.sync()
+        for r, e in enumerate(engs):
+            for side in (0, 1):
+                q = peer(r, side)
+                if q is not None:
+                    e.halo("unpack_" + phase, side, bufs[(q, 1 - side)].data_ptr())
+        for e in engs:
+            e.sync()
+
+    for i in range(nsteps):
+        need = engs[0].next_step_needs_halo()
+        if need:
+            exchange("pre")
+        if case.coll == cases.CM_OPT:
+            if adapter_mode == 0:
+                for e in engs:
+                    e.adapter_prepass()
+            if adapter_mode == 0 or i > 0:
+                tot = sum(e.moment_sums() for e in engs)
+                for e in engs:
+                    e.set_moment_sums(tot)
+        for e in engs:
+            e.step(1, macroscopics=(i == nsteps - 1))
+        for e in engs:
+            e.sync()
+        if need:
+            exchange("post")
+    rho = np.concatenate([e.macroscopics()[0] for e in engs], axis=0)
+    u = np.concatenate([e.macroscopics()[1] for e in engs], axis=0)
+    f = np.concatenate([e.populations() for e in engs], axis=0)
+    for e in engs:
+        e.close()
+    return rho, u, f
+
+
+@pytest.mark.parametrize("name,world", [("g_tg_bgk", 2), ("g_tg_mrt", 3), ("g_tg_cmopt", 2), ("g_pois_mrt", 2), ("g_lid_cm", 3), ("g_lid_cmopt", 2)])
+def test_slabs_match_single_domain(name, world):
+    """The slab-decomposed run reproduces the single-handle run bit for bit (same per-cell arithmetic; OptimalAdapter sums in fp64
+    differ in association only, hence a tolerance there)."""
+    case = cases.BY_NAME[name]
+    nsteps = 7
+    rho_s, u_s, f_s = _run_slabs(case, world, nsteps)
+    e = make_engine(case)
+    e.init_fields(*case.init_fields())
+    e.step(nsteps, macroscopics=True)
+    rho_1, u_1 = e.macroscopics()
+    f_1 = e.populations()
+    e.close()
+    tol = 0.0 if case.coll != cases.CM_OPT else 2e-7
+    assert np.abs(f_s - f_1).max() <= tol, np.abs(f_s - f_1).max()
+    assert np.abs(rho_s - rho_1).max() <= tol and np.abs(u_s - u_1).max() <= tol
