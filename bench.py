@@ -168,7 +168,8 @@ def main():
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     eng.set_stream(stream.cuda_stream)
-    solver = SlabSolver(eng, nx, True, dev, optimal_adapter=(coll == L.CM_OPTIMAL), adapter_exact=False)
+    slab_mode = os.environ.get("LBM_SLAB_MODE", "direct")        # "direct": peer-mapped edge rows over NVLink; "nccl": packed halo rows
+    solver = SlabSolver(eng, nx, True, dev, optimal_adapter=(coll == L.CM_OPTIMAL), adapter_exact=False, mode=slab_mode)
     nloc = eng.ny_local * nx
 
     def barrier():
@@ -185,6 +186,7 @@ def main():
 
     # ---------------- device-resident measurement ----------------
     eng.init_taylor_green(NU, 0.04 / scale)
+    solver.barrier_after_init()
     solver.step(args.warmup)
     barrier()
     l0 = eng.info().kernel_launches
@@ -220,9 +222,11 @@ def main():
         check(lib().lbm_reserve_macroscopics(eng._h))
         eng.init_taylor_green(NU, 0.04 / scale)
         eng.macroscopics_into(h_rho.value, h_u.value)
+        solver.barrier_after_init()
         barrier()
         t0 = time.perf_counter()
         check(lib().lbm_init_fields_local(eng._h, h_rho, h_u))               # H2D of the segment's inputs (pinned host memory)
+        solver.barrier_after_init()
         solver.step(args.steps, macroscopics=True)
         eng.macroscopics_into(h_rho.value, h_u.value)                        # D2H of the result; blocks until done
         barrier()
@@ -246,7 +250,7 @@ def main():
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
                 "config": {"workload": f"taylor_green_d2q9_{args.collision.lower()}_{nx}x{ny}_periodic_yslab", "nx": nx, "ny": ny,
-                           "collision": args.collision, "rows_per_gpu": eng.ny_local, "quirks": "reference-compatible",
+                           "collision": args.collision, "rows_per_gpu": eng.ny_local, "quirks": "reference-compatible", "slab_coupling": solver.mode,
                            "l2_policy": f"populations per GPU {36.0 * nloc / 1e9:.1f} GB >> 126 MB L2 (no flush needed)"},
                 "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -14,6 +14,7 @@ BGK, MRT, CM, CM_OPTIMAL = 0, 1, 2, 3
 QK_D1_STALE_F0, QK_D2_MRT_ROWS, QK_D3_ZOUHE_RHO, QK_D7_IBM_CLIP, QK_D8_IBM_2X2, QK_D11_BB_RAW = 1, 2, 4, 8, 16, 32
 QK_REFERENCE, QK_FIXED = 63, 0
 ADAPTER_EXACT, ADAPTER_LAGGED = 0, 1
+PEER_DESC_BYTES = 128
 FLUID, BOUNCE_BACK, ZOU_HE_TOP, ZOU_HE_LEFT = 0, 1, 2, 3
 CYLINDER, ZG_OUTFLOW, PRESSURE_OUTLET, REGULARIZED_INLET_TOP = 6, 7, 8, 9
 REGULARIZED_BOUNCE_BACK, REGULARIZED_BOUNCE_BACK_CORNER = 11, 12
@@ -25,7 +26,8 @@ SYMBOLS = [
     "lbm_set_populations", "lbm_get_populations", "lbm_step", "lbm_step_with_macroscopics", "lbm_sync",
     "lbm_get_macroscopics", "lbm_get_macroscopics_device", "lbm_reserve_macroscopics", "lbm_total_mass", "lbm_moment_avg", "lbm_adapter_prepass",
     "lbm_set_moment_sums", "lbm_get_moment_sums", "lbm_info", "lbm_next_step_needs_halo", "lbm_halo_pack_pre",
-    "lbm_halo_unpack_pre", "lbm_halo_pack_post", "lbm_halo_unpack_post", "lbm_host_alloc", "lbm_host_free",
+    "lbm_halo_unpack_pre", "lbm_halo_pack_post", "lbm_halo_unpack_post", "lbm_peer_export", "lbm_peer_attach", "lbm_peer_detach",
+    "lbm_host_alloc", "lbm_host_free",
     "lbm_last_error",
 ]
 
@@ -96,6 +98,9 @@ def lib():
         "lbm_halo_unpack_pre": [vp, C.c_int, vp],
         "lbm_halo_pack_post": [vp, C.c_int, vp],
         "lbm_halo_unpack_post": [vp, C.c_int, vp],
+        "lbm_peer_export": [vp, vp],
+        "lbm_peer_attach": [vp, C.c_int, vp],
+        "lbm_peer_detach": [vp],
         "lbm_host_alloc": [C.POINTER(vp), C.c_int64],
         "lbm_host_free": [vp],
     }

@@ -66,10 +66,20 @@ struct Params {
     // IBM nodes, per-node force, non-periodic domain edge); the vectorised kernel skips those and the scalar kernel
     // processes exactly the ones listed in gen_list.
     const uint8_t* segmask; int nsx; const int* gen_list;
+    // direct y-slab coupling over NVLink peer memory: [0] = the lower neighbour's top edge row, [1] = the upper neighbour's
+    // bottom edge row, addressed as peer[s] + plane * peer_plane[s] + peer_off[s] + x.  nullptr = use this slab's ghost rows.
+    float* peer[2]; long long peer_plane[2]; long long peer_off[2];
+    long long plane;        // floats per slot plane of this slab: A[q] == A[0] + q * plane
 };
 constexpr int SEG = 128;
 
 __device__ __forceinline__ long long rowoff(const Params& p, int yl) { return (long long)(yl + 1) * p.nx; }
+// start of row yl of a slot plane; rows -1 and nyl resolve to the neighbour slab's edge row when it is peer-mapped
+__device__ __forceinline__ float* row_ptr(const Params& p, int plane, int yl) {
+    if (yl < 0 && p.peer[0]) return p.peer[0] + plane * p.peer_plane[0] + p.peer_off[0];
+    if (yl >= p.nyl && p.peer[1]) return p.peer[1] + plane * p.peer_plane[1] + p.peer_off[1];
+    return p.A[plane] + rowoff(p, yl);
+}
 
 // Source / destination coordinate of a streaming hop with the reference's per-axis periodic wrap
 // (src/core/streaming/streaming.cu:13-21).  Returns false when the hop leaves a non-periodic domain.
@@ -113,7 +123,7 @@ __device__ __forceinline__ int pull(const Params& p, int x, int yl, float g[Q]) 
         for (int q = 1; q < Q; q++) {
             int xs = x, ys = yl;
             bool ok = hop(p, xs, ys, -cx(q), -cy(q));
-            g[q] = ok ? p.A[opp(q)][rowoff(p, ys) + xs] : 0.0f;
+            g[q] = ok ? row_ptr(p, opp(q), ys)[xs] : 0.0f;
         }
     }
     const int yg = p.y0 + yl;
@@ -144,7 +154,7 @@ __device__ __forceinline__ void push(const Params& p, int x, int yl, int e, cons
         for (int q = 1; q < Q; q++) {
             int xd = x, yd = yl;
             bool ok = hop(p, xd, yd, cx(q), cy(q));
-            if (ok) p.A[q][rowoff(p, yd) + xd] = f[q];
+            if (ok) row_ptr(p, q, yd)[xd] = f[q];
         }
     }
     if (e >= 0) {
@@ -161,7 +171,7 @@ __device__ __forceinline__ float feq(int q, float rho, float ux, float uy, float
     return wq(q) * rho * (1.0f + 3.0f * cu + 4.5f * cu * cu - usq15);
 }
 
-struct Moments { float rho, ux, uy, pxx, pxy, pyy; };
+struct Moments { float rho, inv_rho, ux, uy, pxx, pxy, pyy; };
 
 // uncorrected_macroscopics_kernel<2> — reference src/core/macroscopics/macroscopics.cu:5-38
 __device__ __forceinline__ Moments moments(const float g[Q]) {
@@ -170,6 +180,7 @@ __device__ __forceinline__ Moments moments(const float g[Q]) {
     float jx = (g[1] - g[3]) + (g[5] - g[6]) + (g[8] - g[7]);
     float jy = (g[2] - g[4]) + (g[5] - g[8]) + (g[6] - g[7]);
     float inv = 1.0f / m.rho;
+    m.inv_rho = inv;
     m.ux = jx * inv; m.uy = jy * inv;
     float d = g[5] + g[6] + g[7] + g[8];
     m.pxx = g[1] + g[3] + d;
@@ -403,8 +414,14 @@ __device__ __forceinline__ void collide_mrt(const Params& p, float g[Q], float r
 }
 
 // OptimalAdapter::compute_higher_order_relaxation — reference src/core/collision/adapters.cuh:48-111
-__device__ __forceinline__ float optimal_rate(float rho, float jmag, float pimag, const float* avg) {
-    float ts = 0.0003f * (rho / avg[0]) - 0.00775f * (jmag / avg[1]) + 0.00016f * (pimag / avg[2]) + 0.0087f;
+// The three grid means are the same for every cell of a step, so the divisions become multiplications by reciprocals
+// taken once per thread (<= 1 ulp on a ratio that enters tau* with a weight of 1e-2 .. 1e-4).
+struct AdapterAvg { float inv_rho, inv_j, inv_pi; };
+__device__ __forceinline__ AdapterAvg load_adapter_avg(const float* avg) {
+    AdapterAvg a; a.inv_rho = 1.0f / avg[0]; a.inv_j = 1.0f / avg[1]; a.inv_pi = 1.0f / avg[2]; return a;
+}
+__device__ __forceinline__ float optimal_rate(float rho, float jmag, float pimag, const AdapterAvg& a) {
+    float ts = 0.0003f * (rho * a.inv_rho) - 0.00775f * (jmag * a.inv_j) + 0.00016f * (pimag * a.inv_pi) + 0.0087f;
     ts = ts > 0.0f ? ts : 0.005f;
     ts = fminf(ts, 1.5f);
     return 1.0f / (3.0f * ts + 0.5f);
@@ -414,8 +431,10 @@ __device__ __forceinline__ float optimal_rate(float rho, float jmag, float pimag
 // nine central moments with per-direction polynomials and multiplies by an 81-entry T^-1(u)
 // (cm_matrix_inverse, :141-250, ~900 flop).  Here: raw moments (add chains) -> binomial shift by -u ->
 // relax -> shift by +u -> populations; algebraically identical (tests/test_transforms.py), ~200 flop.
+// jmag = rho |u| and pimag = |Pi| of the cell (only read when OPTIMAL): the same values that enter the grid means.
 template <bool OPTIMAL>
-__device__ __forceinline__ void collide_cm(const Params& p, float g[Q], float ux, float uy, float Fx, float Fy) {
+__device__ __forceinline__ void collide_cm(const Params& p, float g[Q], float ux, float uy, float Fx, float Fy,
+                                           float jmag = 0.f, float pimag = 0.f, const AdapterAvg* avg = nullptr) {
     // raw moments m_ab = sum f cx^a cy^b
     const float d = (g[5] + g[7]) + (g[6] + g[8]);
     const float m00 = g[0] + ((g[1] + g[3]) + (g[2] + g[4])) + d;      // rho recomputed from f (:38-41)
@@ -442,11 +461,7 @@ __device__ __forceinline__ void collide_cm(const Params& p, float g[Q], float ux
     const float keq[Q] = {rho, 0.0f, 0.0f, 2.0f * rho * cs2, 0.0f, 0.0f, 0.0f, 0.0f, rho * cs2 * cs2};
     const float F[Q] = {0.0f, Fx, Fy, 0.0f, 0.0f, 0.0f, Fy * cs2, Fx * cs2, 0.0f};
     float hi = 1.0f;
-    if (OPTIMAL) {
-        float pimag = sqrtf(m20 * m20 + 2.0f * m11 * m11 + m02 * m02);
-        float jmag = sqrtf(ux2 + uy2) * rho;
-        hi = optimal_rate(rho, jmag, pimag, p.avg);
-    }
+    if (OPTIMAL) hi = optimal_rate(rho, jmag, pimag, *avg);
 #pragma unroll
     for (int i = 0; i < Q; i++) {
         float r = (OPTIMAL && i > 5) ? hi : p.S[i];                // AdapterBase::is_higher_order, adapters.cuh:8-13

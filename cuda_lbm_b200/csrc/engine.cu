@@ -22,6 +22,7 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <unistd.h>
 
 #include "../../include/lbm_b200.h"
 #include "kernels.cuh"
@@ -67,7 +68,24 @@ struct lbm_handle {
     long long launches = 0;
     long long bytes = 0;
     float omega = 1.0f;
+    // peer-mapped slab coupling (lbm_peer_export / lbm_peer_attach)
+    unsigned long long* sync_flags = nullptr;      // 2 step counters written by the neighbours + padding, at the end of `pop`
+    int* sync_timeout = nullptr;
+    struct Peer { float* base = nullptr; void* ipc_base = nullptr; long long plane = 0, off = 0; unsigned long long* flag = nullptr; bool attached = false; } peer[2];
+    cudaIpcMemHandle_t peer_ipc[2]{};
+    bool direct() const { return peer[0].attached || peer[1].attached; }
 };
+
+// what one slab tells its neighbours (lbm_peer_export); opaque to callers, LBM_PEER_DESC_BYTES long
+struct PeerDesc {
+    cudaIpcMemHandle_t ipc;         // of the population allocation
+    long long pid;
+    unsigned long long raw;         // device pointer, valid inside the exporting process
+    long long plane;                // floats per slot plane
+    long long flags_off;            // byte offset of the two step counters inside the allocation
+    int nx, nyl, device, rank;
+};
+static_assert(sizeof(PeerDesc) <= LBM_PEER_DESC_BYTES, "PeerDesc must fit the ABI buffer");
 
 template <typename T>
 static cudaError_t dmalloc(lbm_handle* h, T** p, size_t count) {
@@ -94,7 +112,8 @@ static Params make_params(lbm_handle* h, int t) {
     p.nbr_nodes = h->nbr_nodes; p.nbr_g = h->nbr_g; p.nbr_count = h->nbr_count;
     p.ibm_nodes = h->ibm_nodes; p.ibm_force = h->ibm_force; p.ibm_count = h->ibm_count;
     p.avg = h->avg; p.partials = nullptr; p.rho_out = nullptr; p.u_out = nullptr;
-    p.segmask = nullptr; p.nsx = h->nsx; p.gen_list = nullptr;
+    p.segmask = nullptr; p.nsx = h->nsx; p.gen_list = nullptr; p.plane = (long long)h->plane;
+    for (int sd = 0; sd < 2; sd++) { p.peer[sd] = h->peer[sd].attached ? h->peer[sd].base : nullptr; p.peer_plane[sd] = h->peer[sd].plane; p.peer_off[sd] = h->peer[sd].off; }
     return p;
 }
 
@@ -120,7 +139,9 @@ extern "C" int lbm_destroy(lbm_handle* h) {
     if (!h) return LBM_OK;
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    void* ptrs[] = {h->pop, h->flags, h->force_plane, h->ring, h->nbr_nodes, h->nbr_src, h->nbr_g, h->d_pts, h->ibm_nodes,
+    for (int sd = 0; sd < 2; sd++)
+        if (h->peer[sd].ipc_base && !(sd == 1 && h->peer[0].ipc_base == h->peer[1].ipc_base)) cudaIpcCloseMemHandle(h->peer[sd].ipc_base);
+    void* ptrs[] = {h->sync_timeout, h->pop, h->flags, h->force_plane, h->ring, h->nbr_nodes, h->nbr_src, h->nbr_g, h->d_pts, h->ibm_nodes,
                     h->sten_idx, h->sten_w, h->csr_row, h->csr_k, h->csr_w, h->ibm_rho, h->ibm_uprev, h->ibm_lagF, h->ibm_force,
                     h->partials, h->stage, h->sums, h->avg, h->rho_out, h->u_out, h->mass_acc, h->segmask, h->gen_list};
     for (void* p : ptrs) if (p) cudaFree(p);
@@ -160,13 +181,17 @@ extern "C" int lbm_create(const lbm_config* cfg, lbm_handle** out) {
     if (e != cudaSuccess) { delete h; return fail(LBM_ERR_CUDA, cudaGetErrorString(e)); }
     h->stream = h->own_stream;
     h->perim = 2 * cfg->nx + 2 * cfg->ny;
-    bool ok = dmalloc(h, &h->pop, h->plane * h->nplanes) == cudaSuccess &&
+    const size_t pop_floats = h->plane * h->nplanes;
+    bool ok = dmalloc(h, &h->pop, pop_floats + 64) == cudaSuccess &&          // + 256 B: neighbour step counters (exported with the same IPC handle)
+              dmalloc(h, &h->sync_timeout, 1) == cudaSuccess &&
               dmalloc(h, &h->ring, (size_t)2 * h->perim * Q) == cudaSuccess &&
               dmalloc(h, &h->sums, 3) == cudaSuccess && dmalloc(h, &h->avg, 3) == cudaSuccess &&
               dmalloc(h, &h->mass_acc, 1) == cudaSuccess;
     if (ok && cfg->collision == LBM_CM_OPTIMAL) ok = dmalloc(h, &h->stage, (size_t)3 * RED_BLOCKS) == cudaSuccess;
     if (!ok) { std::string m = cudaGetErrorString(cudaGetLastError()); lbm_destroy(h); return fail(LBM_ERR_CUDA, "device allocation failed: " + m); }
-    cudaMemsetAsync(h->pop, 0, h->plane * h->nplanes * sizeof(float), h->stream);
+    cudaMemsetAsync(h->pop, 0, (pop_floats + 64) * sizeof(float), h->stream);
+    cudaMemsetAsync(h->sync_timeout, 0, sizeof(int), h->stream);
+    h->sync_flags = reinterpret_cast<unsigned long long*>(h->pop + pop_floats);
     cudaMemsetAsync(h->ring, 0, (size_t)2 * h->perim * Q * sizeof(float), h->stream);
     float one[3] = {1.f, 1.f, 1.f};
     cudaMemcpyAsync(h->avg, one, sizeof(one), cudaMemcpyHostToDevice, h->stream);
@@ -383,6 +408,7 @@ extern "C" int lbm_init_fields_device(lbm_handle* h, const float* d_rho, const f
     h->launches++;
     CU(cudaGetLastError());
     h->timestep = 0; h->macros_ts = 0; h->avg_for_ts = -1; h->pre_for_ts = -1;
+    CU(cudaMemsetAsync(h->sync_flags, 0, 16, h->stream));
     return LBM_OK;
 }
 
@@ -411,6 +437,7 @@ extern "C" int lbm_init_taylor_green(lbm_handle* h, float nu, float u0) {
     h->launches++;
     CU(cudaGetLastError());
     h->timestep = 0; h->macros_ts = h->rho_out ? 0 : -1; h->avg_for_ts = -1; h->pre_for_ts = -1;
+    CU(cudaMemsetAsync(h->sync_flags, 0, 16, h->stream));
     return LBM_OK;
 }
 
@@ -591,23 +618,59 @@ static int one_step(lbm_handle* h, bool want_macros) {
     return LBM_OK;
 }
 
+static int prepare_resources(lbm_handle* h, bool want_macros);
+
 extern "C" int lbm_adapter_prepass(lbm_handle* h) {
     if (!h) return fail(LBM_ERR_INVALID, "NULL handle");
     if (h->cfg.collision != LBM_CM_OPTIMAL) return LBM_OK;
     CU(cudaSetDevice(h->cfg.device));
+    { int rc0 = prepare_resources(h, false); if (rc0) return rc0; }
+    if (h->direct()) {      // the pre-pass already reads the neighbours' edge rows
+        wait_neighbours_kernel<<<1, 1, 0, h->stream>>>(h->sync_flags, h->peer[0].attached, h->peer[1].attached, (unsigned long long)h->timestep, h->sync_timeout);
+        h->launches++;
+    }
     int rc = pre_passes(h, h->timestep + 1, true); if (rc) return rc;
     CU(cudaGetLastError());
+    return LBM_OK;
+}
+
+// Everything a step may allocate lazily (cudaMalloc synchronises the whole device) is settled here, before the first
+// handshake kernel of a call is enqueued: a wait kernel spinning on one handle's stream while another handle of the same
+// process sits in cudaMalloc would dead-lock until the handshake timeout.
+static int prepare_resources(lbm_handle* h, bool want_macros) {
+    int rc;
+    if (use_vec(h) && is_general(h)) { rc = ensure_segments(h); if (rc) return rc; }
+    if (want_macros) { rc = ensure_macros(h); if (rc) return rc; }
+    if (h->cfg.collision == LBM_CM_OPTIMAL) {
+        dim3 g = grid_of(h);
+        long long n = (long long)g.x * g.y;
+        if (use_vec(h)) { int th; dim3 gv = vec_grid(h, th); n = std::max(n, (long long)gv.x * gv.y + (is_general(h) ? h->gen_count : 0)); }
+        rc = ensure_partials(h, n); if (rc) return rc;
+    }
     return LBM_OK;
 }
 
 static int run_steps(lbm_handle* h, int n, bool macros_last) {
     if (!h) return fail(LBM_ERR_INVALID, "NULL handle");
     if (n < 0) return fail(LBM_ERR_INVALID, "nsteps < 0");
-    if (h->cfg.world > 1 && n > 1) return fail(LBM_ERR_INVALID, "world > 1: step one at a time and exchange halos in between");
+    const bool direct = h->direct();
+    if (h->cfg.world > 1 && n > 1 && !direct) return fail(LBM_ERR_INVALID, "world > 1 without peer-mapped neighbours: step one at a time and exchange halos in between");
+    if (h->cfg.world > 1 && n > 1 && h->cfg.collision == LBM_CM_OPTIMAL) return fail(LBM_ERR_INVALID, "OptimalAdapter on several slabs needs the all-reduce of the grid sums between steps: nsteps must be 1");
     CU(cudaSetDevice(h->cfg.device));
+    if (n > 0) { int rc = prepare_resources(h, macros_last); if (rc) return rc; }
     for (int i = 0; i < n; i++) {
+        if (direct) {
+            // every step touches cells the neighbours wrote (odd: their edge rows, even: what they stored into mine):
+            // wait until both have completed step t-1, and tell them when step t is done
+            wait_neighbours_kernel<<<1, 1, 0, h->stream>>>(h->sync_flags, h->peer[0].attached, h->peer[1].attached, (unsigned long long)h->timestep, h->sync_timeout);
+            h->launches++;
+        }
         int rc = one_step(h, macros_last && i == n - 1);
         if (rc) return rc;
+        if (direct) {
+            signal_neighbours_kernel<<<1, 1, 0, h->stream>>>(h->peer[0].attached ? h->peer[0].flag : nullptr, h->peer[1].attached ? h->peer[1].flag : nullptr, (unsigned long long)h->timestep);
+            h->launches++;
+        }
     }
     CU(cudaGetLastError());
     return LBM_OK;
@@ -620,6 +683,11 @@ extern "C" int lbm_sync(lbm_handle* h) {
     if (!h) return fail(LBM_ERR_INVALID, "NULL handle");
     CU(cudaSetDevice(h->cfg.device));
     CU(cudaStreamSynchronize(h->stream));
+    if (h->direct()) {
+        int to = 0;
+        CU(cudaMemcpy(&to, h->sync_timeout, sizeof(int), cudaMemcpyDeviceToHost));
+        if (to) return fail(LBM_ERR_STATE, "a neighbour slab did not reach the previous time step within 10 s (peer-mapped handshake timed out); results are invalid");
+    }
     return LBM_OK;
 }
 
@@ -698,7 +766,7 @@ static const int kSlots[2][3] = {{4, 7, 8}, {2, 5, 6}};
 
 extern "C" int lbm_next_step_needs_halo(lbm_handle* h) {
     if (!h) return 0;
-    return (h->cfg.world > 1 && ((h->timestep + 1) & 1)) ? 1 : 0;
+    return (h->cfg.world > 1 && !h->direct() && ((h->timestep + 1) & 1)) ? 1 : 0;
 }
 
 static bool has_neighbour(const lbm_handle* h, int side) {
@@ -747,6 +815,66 @@ extern "C" int lbm_halo_unpack_post(lbm_handle* h, int side, const float* buf) {
     if (!has_neighbour(h, side)) return LBM_OK;
     CU(cudaSetDevice(h->cfg.device));
     return copy_rows(h, own_edge_row(h, side), kSlots[1 - side], (float*)buf, false);
+}
+
+// ------------------------------------------------------------------ peer-mapped neighbours (NVLink / same-device)
+extern "C" int lbm_peer_export(lbm_handle* h, void* out) {
+    if (!h || !out) return fail(LBM_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(h->cfg.device));
+    PeerDesc d{};
+    CU(cudaIpcGetMemHandle(&d.ipc, h->pop));
+    d.pid = (long long)getpid(); d.raw = (unsigned long long)(uintptr_t)h->pop; d.plane = (long long)h->plane;
+    d.flags_off = (long long)((char*)h->sync_flags - (char*)h->pop);
+    d.nx = h->cfg.nx; d.nyl = h->nyl; d.device = h->cfg.device; d.rank = h->cfg.rank;
+    memset(out, 0, LBM_PEER_DESC_BYTES);
+    memcpy(out, &d, sizeof(d));
+    return LBM_OK;
+}
+
+extern "C" int lbm_peer_attach(lbm_handle* h, int side, const void* desc) {
+    if (!h || !desc || side < 0 || side > 1) return fail(LBM_ERR_INVALID, "bad argument");
+    if (!has_neighbour(h, side)) return fail(LBM_ERR_INVALID, "this slab has no neighbour on that side");
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaStreamSynchronize(h->stream));
+    PeerDesc d; memcpy(&d, desc, sizeof(d));
+    if (d.nx != h->cfg.nx) return fail(LBM_ERR_INVALID, "neighbour slab has a different nx");
+    lbm_handle::Peer& P = h->peer[side];
+    if (P.attached) return fail(LBM_ERR_STATE, "side already attached");
+    char* base = nullptr;
+    if (d.pid == (long long)getpid()) {
+        base = (char*)(uintptr_t)d.raw;                       // same process: the pointer is valid as it is
+        if (d.device != h->cfg.device) {
+            int can = 0; CU(cudaDeviceCanAccessPeer(&can, h->cfg.device, d.device));
+            if (!can) return fail(LBM_ERR_INVALID, "devices cannot access each other's memory");
+            cudaError_t e = cudaDeviceEnablePeerAccess(d.device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(LBM_ERR_CUDA, cudaGetErrorString(e));
+            cudaGetLastError();
+        }
+    } else {
+        const lbm_handle::Peer& O = h->peer[1 - side];
+        if (O.ipc_base && O.base == (float*)O.ipc_base && memcmp(&d.ipc, &h->peer_ipc[1 - side], sizeof(d.ipc)) == 0) base = (char*)O.ipc_base;   // world == 2, periodic: both faces touch the same slab
+        else CU(cudaIpcOpenMemHandle((void**)&base, d.ipc, cudaIpcMemLazyEnablePeerAccess));
+        P.ipc_base = base;
+        h->peer_ipc[side] = d.ipc;
+    }
+    P.base = (float*)base; P.plane = d.plane;
+    // side 0 (lower neighbour): its top edge row = local row nyl-1 -> plane row nyl; side 1: its local row 0 -> plane row 1
+    P.off = (side == 0 ? (long long)d.nyl : 1ll) * d.nx;
+    // I am the neighbour's upper peer when it is below me: it waits on its flags[1]
+    P.flag = reinterpret_cast<unsigned long long*>(base + d.flags_off) + (side == 0 ? 1 : 0);
+    P.attached = true;
+    return prepare_resources(h, false);
+}
+
+extern "C" int lbm_peer_detach(lbm_handle* h) {
+    if (!h) return fail(LBM_ERR_INVALID, "NULL handle");
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaStreamSynchronize(h->stream));
+    for (int sd = 0; sd < 2; sd++) {
+        if (h->peer[sd].ipc_base && !(sd == 1 && h->peer[0].ipc_base == h->peer[1].ipc_base)) cudaIpcCloseMemHandle(h->peer[sd].ipc_base);
+        h->peer[sd] = lbm_handle::Peer();
+    }
+    return LBM_OK;
 }
 
 extern "C" int lbm_host_alloc(void** out, int64_t bytes) {

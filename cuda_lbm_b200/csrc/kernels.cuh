@@ -32,7 +32,7 @@ __device__ __forceinline__ void node_pre_collision(const Params& p, int x, int y
         }
     }
     // correct_macroscopics_kernel<2> (macroscopics.cu:99-110): u += F / (2 rho)
-    const float h = 0.5f / s.m.rho;
+    const float h = 0.5f * s.m.inv_rho;               // == 0.5f / rho bit for bit (scaling by a power of two)
     s.ux = s.m.ux + s.Fx * h; s.uy = s.m.uy + s.Fy * h;
 }
 
@@ -81,11 +81,11 @@ __global__ void __launch_bounds__(BX) step_kernel(const Params p) {
             p.rho_out[ln] = s.m.rho;
             p.u_out[ln] = make_float2(s.ux, s.uy);
         }
-        if (COLL == C_CMOPT) { s0 = s.m.rho; s1 = s.m.rho * sqrtf(s.ux * s.ux + s.uy * s.uy); s2 = pi_norm(s.m); }
+        if (COLL == C_CMOPT) { s0 = s.m.rho; s1 = sqrtf(s.ux * s.ux + s.uy * s.uy) * s.m.rho; s2 = pi_norm(s.m); }
         if (COLL == C_BGK) collide_bgk(p, s.g, s.m.rho, s.ux, s.uy, s.Fx, s.Fy);
         else if (COLL == C_MRT) collide_mrt(p, s.g, s.m.rho, s.ux, s.uy, s.Fx, s.Fy);
         else if (COLL == C_CM) collide_cm<false>(p, s.g, s.ux, s.uy, s.Fx, s.Fy);
-        else collide_cm<true>(p, s.g, s.ux, s.uy, s.Fx, s.Fy);
+        else { const AdapterAvg av = load_adapter_avg(p.avg); collide_cm<true>(p, s.g, s.ux, s.uy, s.Fx, s.Fy, s1, s2, &av); }
         push<ODD>(p, x, yl, s.e, s.g);
     }
     if (COLL == C_CMOPT && p.partials) block_partials(s0, s1, s2, p.partials + 3 * ((long long)blockIdx.y * gridDim.x + blockIdx.x));
@@ -100,24 +100,17 @@ __global__ void __launch_bounds__(BX) step_kernel(const Params p) {
 //              plane and the one element that crosses the 16-byte boundary moves between neighbouring lanes with a
 //              warp shuffle; only the first / last lane of a warp (or of a row) touch the odd element with a scalar access.
 constexpr unsigned FULL = 0xffffffffu;
+// 128-thread blocks per SM the register allocator must allow (even / odd AA phase)
+#ifndef LBM_VEC_MIN_BLOCKS_EVEN
+#define LBM_VEC_MIN_BLOCKS_EVEN 6
+#endif
+#ifndef LBM_VEC_MIN_BLOCKS_ODD
+#define LBM_VEC_MIN_BLOCKS_ODD 5
+#endif
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float a, float b, float c, float d) { *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d); }
 
-// values of plane row `r` at x0-1 .. x0+2 (source of a population moving in +x)
-__device__ __forceinline__ void load_from_left(const float* r, int x0, int xl, bool hasL, float o[4]) {
-    const float4 v = ld4(r + x0);
-    float l = __shfl_up_sync(FULL, v.w, 1);
-    if (!hasL) l = r[xl];
-    o[0] = l; o[1] = v.x; o[2] = v.y; o[3] = v.z;
-}
-// values at x0+1 .. x0+4 (source of a population moving in -x)
-__device__ __forceinline__ void load_from_right(const float* r, int x0, int xr, bool hasR, float o[4]) {
-    const float4 v = ld4(r + x0);
-    float rr = __shfl_down_sync(FULL, v.x, 1);
-    if (!hasR) rr = r[xr];
-    o[0] = v.y; o[1] = v.z; o[2] = v.w; o[3] = rr;
-}
 // f[0..3] of cells x0..x0+3 go to x0+1 .. x0+4
 __device__ __forceinline__ void store_to_right(float* r, int x0, int xr, bool hasL, bool hasR, bool act, const float f[4]) {
     const float l = __shfl_up_sync(FULL, f[3], 1);
@@ -136,7 +129,7 @@ __device__ __forceinline__ void store_to_left(float* r, int x0, int xl, bool has
 }
 
 template <int COLL, bool ODD>
-__global__ void __launch_bounds__(BX) step_vec_kernel(const Params p) {
+__global__ void __launch_bounds__(BX, ODD ? LBM_VEC_MIN_BLOCKS_ODD : LBM_VEC_MIN_BLOCKS_EVEN) step_vec_kernel(const Params p) {
     const int nv = p.nx >> 2;
     const int xv_raw = blockIdx.x * blockDim.x + threadIdx.x;
     const int yl = blockIdx.y;
@@ -156,7 +149,15 @@ __global__ void __launch_bounds__(BX) step_vec_kernel(const Params p) {
         int xl = x0 - 1, xr = x0 + 4;
         if (xl < 0) xl += p.nx;
         if (xr >= p.nx) xr -= p.nx;
-        long long rm = 0, rp = 0;
+        int ym = yl - 1, yp = yl + 1;
+        if (p.wrap_y) { if (ym < 0) ym += p.nyl; if (yp >= p.nyl) yp -= p.nyl; }
+        // rows y-1 / y+1 of plane k start at bm + k*sm / bp + k*sp: this slab, its ghost rows, or (peer-mapped) the neighbour slab
+        float* bm = p.A[0] + rowoff(p, ym); long long sm = p.plane;
+        float* bp = p.A[0] + rowoff(p, yp); long long sp = p.plane;
+        if (ODD) {
+            if (ym < 0 && p.peer[0]) { bm = p.peer[0] + p.peer_off[0]; sm = p.peer_plane[0]; }
+            if (yp >= p.nyl && p.peer[1]) { bp = p.peer[1] + p.peer_off[1]; sp = p.peer_plane[1]; }
+        }
         {
             float4 v = ld4(p.A0[gen] + r0 + x0);
             g[0][0] = v.x; g[1][0] = v.y; g[2][0] = v.z; g[3][0] = v.w;
@@ -168,33 +169,49 @@ __global__ void __launch_bounds__(BX) step_vec_kernel(const Params p) {
                 g[0][q] = v.x; g[1][q] = v.y; g[2][q] = v.z; g[3][q] = v.w;
             }
         } else {
-            int ym = yl - 1, yp = yl + 1;
-            if (p.wrap_y) { if (ym < 0) ym += p.nyl; if (yp >= p.nyl) yp -= p.nyl; }
-            rm = rowoff(p, ym); rp = rowoff(p, yp);
+            // g_q(x) = A[opp q][x - c_q]: source row y - c_y, source column x - c_x.  All vector loads first, then the
+            // (predicated) scalar loads of the first / last lane, then the shuffles -- nothing between the loads that
+            // would make them wait for one another.
+            float4 v[Q]; float e[Q];
 #pragma unroll
             for (int q = 1; q < Q; q++) {
-                // g_q(x) = A[opp q][x - c_q]: source row y - c_y, source column x - c_x
-                const float* r = p.A[opp(q)] + (cy(q) > 0 ? rm : (cy(q) < 0 ? rp : r0));
-                float o[4];
-                if (cx(q) > 0) load_from_left(r, x0, xl, hasL, o);
-                else if (cx(q) < 0) load_from_right(r, x0, xr, hasR, o);
-                else { float4 v = ld4(r + x0); o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
-                g[0][q] = o[0]; g[1][q] = o[1]; g[2][q] = o[2]; g[3][q] = o[3];
+                const float* r = cy(q) > 0 ? bm + opp(q) * sm : (cy(q) < 0 ? bp + opp(q) * sp : p.A[opp(q)] + r0);
+                v[q] = ld4(r + x0);
+                e[q] = 0.f;
+                if (cx(q) > 0) { if (!hasL) e[q] = r[xl]; }
+                else if (cx(q) < 0) { if (!hasR) e[q] = r[xr]; }
+            }
+#pragma unroll
+            for (int q = 1; q < Q; q++) {
+                if (cx(q) > 0) {
+                    float l = __shfl_up_sync(FULL, v[q].w, 1);
+                    if (!hasL) l = e[q];
+                    g[0][q] = l; g[1][q] = v[q].x; g[2][q] = v[q].y; g[3][q] = v[q].z;
+                } else if (cx(q) < 0) {
+                    float rr = __shfl_down_sync(FULL, v[q].x, 1);
+                    if (!hasR) rr = e[q];
+                    g[0][q] = v[q].y; g[1][q] = v[q].z; g[2][q] = v[q].w; g[3][q] = rr;
+                } else { g[0][q] = v[q].x; g[1][q] = v[q].y; g[2][q] = v[q].z; g[3][q] = v[q].w; }
             }
         }
         float rho4[4], ux4[4], uy4[4];
+        AdapterAvg av{};
+        if (COLL == C_CMOPT) av = load_adapter_avg(p.avg);
 #pragma unroll
         for (int c = 0; c < 4; c++) {
             Moments m = moments(g[c]);
             const float Fx = p.fx, Fy = p.fy;
-            const float h = 0.5f / m.rho;
+            const float h = 0.5f * m.inv_rho;
             const float ux = m.ux + Fx * h, uy = m.uy + Fy * h;
             rho4[c] = m.rho; ux4[c] = ux; uy4[c] = uy;
-            if (COLL == C_CMOPT && act) { s0 += m.rho; s1 += m.rho * sqrtf(ux * ux + uy * uy); s2 += pi_norm(m); }
             if (COLL == C_BGK) collide_bgk(p, g[c], m.rho, ux, uy, Fx, Fy);
             else if (COLL == C_MRT) collide_mrt(p, g[c], m.rho, ux, uy, Fx, Fy);
             else if (COLL == C_CM) collide_cm<false>(p, g[c], ux, uy, Fx, Fy);
-            else collide_cm<true>(p, g[c], ux, uy, Fx, Fy);
+            else {
+                const float jmag = sqrtf(ux * ux + uy * uy) * m.rho, pimag = pi_norm(m);
+                if (act) { s0 += m.rho; s1 += jmag; s2 += pimag; }
+                collide_cm<true>(p, g[c], ux, uy, Fx, Fy, jmag, pimag, &av);
+            }
         }
         if (p.rho_out && act) {
             const long long ln = (long long)yl * p.nx + x0;
@@ -213,7 +230,7 @@ __global__ void __launch_bounds__(BX) step_vec_kernel(const Params p) {
 #pragma unroll
             for (int q = 1; q < Q; q++) {
                 // f*_q(x) -> A[q][x + c_q]: destination row y + c_y, destination column x + c_x
-                float* r = p.A[q] + (cy(q) > 0 ? rp : (cy(q) < 0 ? rm : r0));
+                float* r = cy(q) > 0 ? bp + q * sp : (cy(q) < 0 ? bm + q * sm : p.A[q] + r0);
                 const float f[4] = {g[0][q], g[1][q], g[2][q], g[3][q]};
                 if (cx(q) > 0) store_to_right(r, x0, xr, hasL, hasR, act, f);
                 else if (cx(q) < 0) store_to_left(r, x0, xl, hasL, hasR, act, f);
@@ -233,7 +250,7 @@ __global__ void __launch_bounds__(BX) moments_kernel(const Params p) {
     if (x < p.nx) {
         NodeState s;
         node_pre_collision<ODD, true>(p, x, yl, s);
-        s0 = s.m.rho; s1 = s.m.rho * sqrtf(s.ux * s.ux + s.uy * s.uy); s2 = pi_norm(s.m);
+        s0 = s.m.rho; s1 = sqrtf(s.ux * s.ux + s.uy * s.uy) * s.m.rho; s2 = pi_norm(s.m);
     }
     block_partials(s0, s1, s2, p.partials + 3 * ((long long)blockIdx.y * gridDim.x + blockIdx.x));
 }
@@ -283,6 +300,22 @@ __global__ void nbr_gather_kernel(const Params p, const long long* nbr_src, floa
     pull<ODD>(p, x, yg - p.y0, g);
 #pragma unroll
     for (int q = 0; q < Q; q++) nbr_g[(long long)k * Q + q] = g[q];
+}
+
+// ---- slab-to-slab step handshake for the peer-mapped mode (one thread each; flags live in the exporting slab's memory)
+// flags[0] / flags[1]: last step completed by the lower / upper neighbour, written by that neighbour over NVLink.
+__global__ void wait_neighbours_kernel(volatile unsigned long long* flags, int need_lo, int need_hi, unsigned long long t, int* timed_out) {
+    const long long t0 = clock64();
+    while ((need_lo && flags[0] < t) || (need_hi && flags[1] < t)) {
+        if (clock64() - t0 > 20000000000ll) { *timed_out = 1; break; }       // ~10 s: a lost neighbour must not hang the GPU
+        __nanosleep(200);
+    }
+}
+__global__ void signal_neighbours_kernel(unsigned long long* lo_flag, unsigned long long* hi_flag, unsigned long long t) {
+    __threadfence_system();
+    if (lo_flag) *(volatile unsigned long long*)lo_flag = t;
+    if (hi_flag) *(volatile unsigned long long*)hi_flag = t;
+    __threadfence_system();
 }
 
 // one thread per segment: does any of its cells need the general path?
@@ -480,7 +513,7 @@ __device__ __forceinline__ void read_post_collision(const Params& p, int x, int 
         for (int q = 1; q < Q; q++) {
             int xd = x, yd = yl;
             bool ok = hop(p, xd, yd, cx(q), cy(q));
-            f[q] = ok ? p.A[q][rowoff(p, yd) + xd] : p.ring[((long long)gen * p.perim + e) * Q + q];
+            f[q] = ok ? row_ptr(p, q, yd)[xd] : p.ring[((long long)gen * p.perim + e) * Q + q];
         }
     }
 }

@@ -70,10 +70,28 @@ class SlabExchange:
                 self.e.halo("unpack_" + phase, side, self.recv[side].data_ptr())
 
 
-class SlabSolver:
-    """The solver loop of one rank: lbm_step one step at a time with halos in between."""
+def attach_peers(engine, periodic_y, group=None):
+    """Peer-mapped coupling (include/lbm_b200.h, lbm_peer_*): every rank exports the descriptor of its population
+    buffer, all-gathers them and attaches its two y-neighbours.  Afterwards the fused kernel reads / writes the
+    neighbour's edge rows over NVLink itself and `engine.step(n)` needs no host-side exchange."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    descs = [None] * world
+    dist.all_gather_object(descs, engine.peer_export(), group=group)
+    lo, hi = neighbours(rank, world, periodic_y)
+    if lo is not None:
+        engine.peer_attach(0, descs[lo])
+    if hi is not None:
+        engine.peer_attach(1, descs[hi])
+    dist.barrier(group=group)
+    return lo, hi
 
-    def __init__(self, engine, nx, periodic_y, device, optimal_adapter=False, adapter_exact=True, group=None):
+
+class SlabSolver:
+    """The solver loop of one rank.  mode "direct": neighbours' edge rows are peer-mapped (NVLink loads/stores inside the
+    fused kernel, device-side step handshake) and n steps are enqueued at once; mode "nccl": lbm_step one step at a
+    time with packed halo rows sent through torch.distributed in between."""
+
+    def __init__(self, engine, nx, periodic_y, device, optimal_adapter=False, adapter_exact=True, group=None, mode="nccl"):
         self.e = engine
         self.x = SlabExchange(engine, nx, periodic_y, device, group=group)
         self.world = self.x.world
@@ -81,6 +99,15 @@ class SlabSolver:
         self.group = group
         self._sums = torch.zeros(3, dtype=torch.float64, device=device)
         self.collectives = 0
+        self.mode = mode if self.world > 1 else "single"
+        if self.mode == "direct":
+            attach_peers(engine, periodic_y, group)
+
+    def barrier_after_init(self):
+        """All slabs must hold their initial state before any of them steps (the handshake counters restart at 0)."""
+        self.e.sync()
+        if self.world > 1:
+            dist.barrier(group=self.group)
 
     def _allreduce_sums(self):
         s = torch.tensor(self.e.moment_sums(), dtype=torch.float64, device=self._sums.device)
@@ -89,7 +116,7 @@ class SlabSolver:
         self.collectives += 1
 
     def step(self, n=1, macroscopics=False):
-        if self.world == 1:
+        if self.world == 1 or (self.mode == "direct" and not self.optimal):
             self.e.step(n, macroscopics=macroscopics)
             return
         for i in range(n):

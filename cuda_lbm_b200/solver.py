@@ -155,6 +155,19 @@ class Engine:
     def adapter_prepass(self):
         check(lib().lbm_adapter_prepass(self._h))
 
+    # --- peer-mapped neighbours ---
+    def peer_export(self):
+        buf = (C.c_ubyte * capi.PEER_DESC_BYTES)()
+        check(lib().lbm_peer_export(self._h, buf))
+        return bytes(buf)
+
+    def peer_attach(self, side, desc):
+        buf = (C.c_ubyte * capi.PEER_DESC_BYTES).from_buffer_copy(desc)
+        check(lib().lbm_peer_attach(self._h, side, buf))
+
+    def peer_detach(self):
+        check(lib().lbm_peer_detach(self._h))
+
     # --- slab halos (device pointers as ints) ---
     def next_step_needs_halo(self):
         return bool(lib().lbm_next_step_needs_halo(self._h))

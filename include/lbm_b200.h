@@ -191,6 +191,20 @@ int lbm_halo_unpack_pre(lbm_handle* h, int side, const float* d_buf);
 int lbm_halo_pack_post(lbm_handle* h, int side, float* d_buf);
 int lbm_halo_unpack_post(lbm_handle* h, int side, const float* d_buf);
 
+/* ---- peer-mapped neighbours: halo rows without copies (no reference counterpart; SURVEY.md §5, §8e option 1) --------
+ * Each slab exports a descriptor of its population buffer (a CUDA IPC handle when the neighbour lives in another
+ * process, the plain device pointer when it lives in this one); the caller moves the LBM_PEER_DESC_BYTES to the two
+ * neighbours (torch.distributed all_gather in cuda_lbm_b200/slab.py) and attaches them: side 0 = lower-y neighbour,
+ * 1 = upper-y neighbour.  From then on the odd (neighbour) steps load and store the three populations that cross a slab
+ * face directly in the neighbour's edge row over NVLink, inside the fused kernel, and every step is bracketed by a
+ * device-side handshake (a step counter each slab writes into its neighbours' memory), so lbm_step(h, n) runs n steps
+ * without host involvement and lbm_halo_* are not needed.  All slabs must have finished lbm_init_* (lbm_sync + a host
+ * barrier) before any of them steps.  A neighbour that never arrives makes lbm_sync fail after 10 s instead of hanging. */
+#define LBM_PEER_DESC_BYTES 128
+int lbm_peer_export(lbm_handle* h, void* desc);
+int lbm_peer_attach(lbm_handle* h, int side, const void* desc);
+int lbm_peer_detach(lbm_handle* h);
+
 /* Pinned host memory helpers for callers that want full-speed host<->device copies. */
 int lbm_host_alloc(void** out, int64_t bytes);
 int lbm_host_free(void* p);

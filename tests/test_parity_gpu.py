@@ -118,7 +118,7 @@ def test_mixed_vector_and_general_segments(kind, nx, ny, periodic, coll):
 
 
 # ---------------------------------------------------------------- y-slabs on one GPU: two/three handles + the halo API
-def _run_slabs(case, world, nsteps, adapter_mode=0):
+def _run_slabs(case, world, nsteps, adapter_mode=0, direct=False, chunk=1):
     """world handles on cuda:0 stepping in lock-step; halos moved through plain device buffers (what NCCL does in slab.py)."""
     import torch
     rho0, u0 = case.init_fields()
@@ -126,6 +126,15 @@ def _run_slabs(case, world, nsteps, adapter_mode=0):
     for e in engs:
         e.init_fields(rho0, u0)
     nx = case.nx
+    py0 = case.periodic[1]
+    if direct:
+        descs = [e.peer_export() for e in engs]
+        for r, e in enumerate(engs):
+            for side, q in ((0, r - 1), (1, r + 1)):
+                if 0 <= q < world or py0:
+                    e.peer_attach(side, descs[q % world])
+        for e in engs:
+            e.sync()
     bufs = {(r, s): torch.zeros(3 * nx, dtype=torch.float32, device="cuda") for r in range(world) for s in (0, 1)}
     py = case.periodic[1]
 
@@ -150,6 +159,16 @@ def _run_slabs(case, world, nsteps, adapter_mode=0):
         for e in engs:
             e.sync()
 
+    if direct and case.coll != cases.CM_OPT:
+        done = 0
+        while done < nsteps:
+            n = min(chunk, nsteps - done)
+            for e in engs:
+                e.step(n, macroscopics=(done + n == nsteps))
+            done += n
+        for e in engs:
+            e.sync()
+        nsteps = 0
     for i in range(nsteps):
         need = engs[0].next_step_needs_halo()
         if need:
@@ -192,3 +211,40 @@ def test_slabs_match_single_domain(name, world):
     tol = 0.0 if case.coll != cases.CM_OPT else 2e-7
     assert np.abs(f_s - f_1).max() <= tol, np.abs(f_s - f_1).max()
     assert np.abs(rho_s - rho_1).max() <= tol and np.abs(u_s - u_1).max() <= tol
+
+
+@pytest.mark.parametrize("name,world,chunk", [("g_tg_bgk", 2, 1), ("g_tg_mrt", 3, 4), ("g_tg_cmopt", 2, 1), ("g_pois_mrt", 2, 7), ("g_lid_cm", 3, 2),
+                                              ("g_lid_cmopt", 3, 1)])
+def test_peer_mapped_slabs_match_single_domain(name, world, chunk):
+    """Same, with the neighbours' edge rows peer-mapped (lbm_peer_*): no halo copies, device-side step handshake,
+    several steps enqueued per call."""
+    case = cases.BY_NAME[name]
+    nsteps = 7
+    rho_s, u_s, f_s = _run_slabs(case, world, nsteps, direct=True, chunk=chunk)
+    e = make_engine(case)
+    e.init_fields(*case.init_fields())
+    e.step(nsteps, macroscopics=True)
+    rho_1, u_1 = e.macroscopics()
+    f_1 = e.populations()
+    e.close()
+    tol = 0.0 if case.coll != cases.CM_OPT else 2e-7
+    assert np.abs(f_s - f_1).max() <= tol, np.abs(f_s - f_1).max()
+    assert np.abs(rho_s - rho_1).max() <= tol and np.abs(u_s - u_1).max() <= tol
+
+
+def test_peer_handshake_times_out_instead_of_hanging():
+    """A slab whose neighbour never steps must come back with an error after the handshake timeout, not hang the GPU."""
+    import cuda_lbm_b200 as L
+    case = cases.BY_NAME["g_tg_bgk"]
+    engs = [make_engine(case, rank=r, world=2) for r in range(2)]
+    for e in engs:
+        e.init_fields(*case.init_fields())
+    d = [e.peer_export() for e in engs]
+    for r, e in enumerate(engs):
+        e.peer_attach(0, d[1 - r]); e.peer_attach(1, d[1 - r])
+    engs[0].step(1)          # fine: needs the neighbour's step 0 = its initial state
+    engs[0].step(1)          # needs the neighbour's step 1, which never comes
+    with pytest.raises(L.LbmError):
+        engs[0].sync()
+    for e in engs:
+        e.close()
