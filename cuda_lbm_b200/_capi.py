@@ -21,7 +21,7 @@ REGULARIZED_BOUNCE_BACK, REGULARIZED_BOUNCE_BACK_CORNER = 11, 12
 
 # every symbol include/lbm_b200.h declares (tests/test_capi_symbols.py checks the header against this list)
 SYMBOLS = [
-    "lbm_default_config", "lbm_create", "lbm_destroy", "lbm_set_stream", "lbm_set_flags", "lbm_set_force_field",
+    "lbm_default_config", "lbm_create", "lbm_destroy", "lbm_set_stream", "lbm_set_flags", "lbm_set_force_field", "lbm_set_force_field_device",
     "lbm_set_body_force", "lbm_add_body", "lbm_init_fields", "lbm_init_fields_local", "lbm_init_fields_device", "lbm_init_taylor_green",
     "lbm_set_populations", "lbm_get_populations", "lbm_step", "lbm_step_with_macroscopics", "lbm_sync",
     "lbm_get_macroscopics", "lbm_get_macroscopics_device", "lbm_reserve_macroscopics", "lbm_total_mass", "lbm_moment_avg", "lbm_adapter_prepass",
@@ -73,6 +73,7 @@ def lib():
         "lbm_set_stream": [vp, vp],
         "lbm_set_flags": [vp, ip],
         "lbm_set_force_field": [vp, fp],
+        "lbm_set_force_field_device": [vp, vp],
         "lbm_set_body_force": [vp, C.c_float, C.c_float],
         "lbm_add_body": [vp, fp, C.c_int32],
         "lbm_init_fields": [vp, fp, fp],

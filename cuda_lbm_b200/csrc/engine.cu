@@ -291,6 +291,16 @@ extern "C" int lbm_set_force_field(lbm_handle* h, const float* force_aos) {
     return LBM_OK;
 }
 
+extern "C" int lbm_set_force_field_device(lbm_handle* h, const float* d_force) {
+    if (!h || !d_force) return fail(LBM_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(h->cfg.device));
+    h->segs_dirty = true;
+    if (!h->force_plane) CU(dmalloc(h, &h->force_plane, (size_t)h->nloc));
+    CU(cudaMemcpyAsync(h->force_plane, d_force, (size_t)h->nloc * sizeof(float2), cudaMemcpyDeviceToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return LBM_OK;
+}
+
 // ------------------------------------------------------------------ IBM structure, built on the GPU
 __global__ void mark_ibm_kernel(uint8_t* flags, const long long* nodes, int n, long long node0, int set) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -117,6 +117,9 @@ int lbm_set_flags(lbm_handle* h, const int32_t* flags);
 /* Optional per-node body force (AoS [node*2+c], global grid, host memory) for scenarios whose
  * apply_forces is not uniform; NULL returns to the uniform cfg.force_x/force_y. */
 int lbm_set_force_field(lbm_handle* h, const float* force_aos);
+/* Same, from device memory holding only this slab's rows (ny_local*nx float2, AoS): what the header shim's
+ * reset_forces<Scenario>() produces by running Init::apply_forces on the device (src/core/macroscopics/macroscopics.cuh:13-48). */
+int lbm_set_force_field_device(lbm_handle* h, const float* d_force_aos_local);
 int lbm_set_body_force(lbm_handle* h, float fx, float fy);
 
 /* Scenario::add_bodies() + IBMManager<2>::init_and_dispatch — src/IBM/IBMManager.cuh:54-109.
