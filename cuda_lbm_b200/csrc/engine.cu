@@ -663,13 +663,16 @@ static int prepare_resources(lbm_handle* h, bool want_macros) {
 static int run_steps(lbm_handle* h, int n, bool macros_last) {
     if (!h) return fail(LBM_ERR_INVALID, "NULL handle");
     if (n < 0) return fail(LBM_ERR_INVALID, "nsteps < 0");
+    // LBM_B200_NO_HANDSHAKE=1 (diagnosis only): skip the device-side step handshake; results are then racy
+    static const bool no_handshake = getenv("LBM_B200_NO_HANDSHAKE") != nullptr;
     const bool direct = h->direct();
+    const bool handshake = direct && !no_handshake;
     if (h->cfg.world > 1 && n > 1 && !direct) return fail(LBM_ERR_INVALID, "world > 1 without peer-mapped neighbours: step one at a time and exchange halos in between");
     if (h->cfg.world > 1 && n > 1 && h->cfg.collision == LBM_CM_OPTIMAL) return fail(LBM_ERR_INVALID, "OptimalAdapter on several slabs needs the all-reduce of the grid sums between steps: nsteps must be 1");
     CU(cudaSetDevice(h->cfg.device));
     if (n > 0) { int rc = prepare_resources(h, macros_last); if (rc) return rc; }
     for (int i = 0; i < n; i++) {
-        if (direct) {
+        if (handshake) {
             // every step touches cells the neighbours wrote (odd: their edge rows, even: what they stored into mine):
             // wait until both have completed step t-1, and tell them when step t is done
             wait_neighbours_kernel<<<1, 1, 0, h->stream>>>(h->sync_flags, h->peer[0].attached, h->peer[1].attached, (unsigned long long)h->timestep, h->sync_timeout);
@@ -677,7 +680,7 @@ static int run_steps(lbm_handle* h, int n, bool macros_last) {
         }
         int rc = one_step(h, macros_last && i == n - 1);
         if (rc) return rc;
-        if (direct) {
+        if (handshake) {
             signal_neighbours_kernel<<<1, 1, 0, h->stream>>>(h->peer[0].attached ? h->peer[0].flag : nullptr, h->peer[1].attached ? h->peer[1].flag : nullptr, (unsigned long long)h->timestep);
             h->launches++;
         }

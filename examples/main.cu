@@ -1,0 +1,113 @@
+// examples/main.cu — main.cu-style driver for the header shim (include/cuda-lbm/): the time loop of the reference's
+// src/main.cu:72-153 written against the same LBM<2> / ScenarioTrait interface, with run-time step counts and a
+// machine-readable result line.  Build one binary per (scenario, NX, NY) — scenario functors bake the grid in as macros:
+//
+//   nvcc -gencode arch=compute_100a,code=sm_100a -std=c++17 -Iinclude/cuda-lbm -I<dir with scenarios/...> \
+//        -DUSE_TAYLOR_GREEN -DPERIODIC_X -DPERIODIC_Y examples/main.cu -Lcuda_lbm_b200 -llbm_b200 -o tg
+//
+// <dir with scenarios/...> is the reference's src/ (its scenario files compile unchanged) or examples/ (this repo's own).
+// Any other scenario:  -DSCENARIO_HEADER='"my/scenario.cuh"' -DSCENARIO_TYPE=MyScenario -DNX=.. -DNY=..
+//
+//   ./tg [--steps N] [--save-int K] [--vtk] [--dump] [--fast]
+//     --save-int K  every K steps: update_macroscopics + compute_error (and --vtk: save_vtk, --dump: save_macroscopics)
+//     --fast        no per-step host calls between save points (LBM::run), the throughput mode
+#include <stdio.h>
+#include <cstring>
+#include <iostream>
+#include "core/lbm.cuh"
+#include "functors/includes.cuh"
+#include "util/timer.cuh"
+#include "IBM/IBMBody.cuh"
+
+#if defined(SCENARIO_HEADER)
+#include SCENARIO_HEADER
+using Scenario = SCENARIO_TYPE;
+#elif defined(USE_TAYLOR_GREEN)
+#include "scenarios/taylorGreen/taylorGreenScenario.cuh"
+using Scenario = TaylorGreenScenario;
+#elif defined(USE_POISEUILLE)
+#include "scenarios/poiseuille/poiseuilleScenario.cuh"
+using Scenario = PoiseuilleScenario;
+#elif defined(USE_LID_DRIVEN)
+#include "scenarios/lidDrivenCavity/lidDrivenCavityScenario.cuh"
+using Scenario = LidDrivenScenario;
+#elif defined(USE_FLOW_PAST_CYLINDER)
+#include "scenarios/flowPastCylinder/flowPastCylinderScenario.cuh"
+using Scenario = FlowPastCylinderScenario;
+#else
+#error "select a scenario: -DUSE_TAYLOR_GREEN / -DUSE_POISEUILLE / -DUSE_LID_DRIVEN / -DUSE_FLOW_PAST_CYLINDER or -DSCENARIO_HEADER/-DSCENARIO_TYPE"
+#endif
+
+int main(int argc, char** argv) {
+    int total_timesteps = 1000, save_int = 100;
+    bool vtk = false, dump = false, fast = false;
+    for (int i = 1; i < argc; i++) {
+        if (!strcmp(argv[i], "--steps") && i + 1 < argc) total_timesteps = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "--save-int") && i + 1 < argc) save_int = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "--vtk")) vtk = true;
+        else if (!strcmp(argv[i], "--dump")) dump = true;
+        else if (!strcmp(argv[i], "--fast")) fast = true;
+        else { fprintf(stderr, "unknown argument %s\n", argv[i]); return 2; }
+    }
+    if (save_int <= 0) save_int = total_timesteps;
+    checkCudaErrors(cudaSetDevice(0));
+    cudaDeviceProp prop;
+    checkCudaErrors(cudaGetDeviceProperties(&prop, 0));
+    constexpr float Re = compute_reynolds(Scenario::u_max, NY, Scenario::viscosity);
+    std::cout << "Running " << Scenario::name() << " scenario on " << prop.name << ", " << NX << " x " << NY << std::endl;
+    std::cout << "Viscosity: " << Scenario::viscosity << ", Tau: " << Scenario::tau << std::endl;
+    std::cout << "Reynolds number: " << Re << std::endl;
+
+    LBM<dimensions> lbm;
+    lbm.allocate<Scenario>();
+    lbm.init<Scenario>();
+
+    cudaEvent_t start, stop;
+    cudaEventCreate(&start);
+    cudaEventCreate(&stop);
+    float last_error = -1.0f, gpu_ms = 0.0f;
+    int t = 0;
+    while (t < total_timesteps) {
+        const int chunk = std::min(save_int, total_timesteps - t);
+        cudaEventRecord(start);
+        if (fast) {
+            lbm.run<Scenario>(chunk);
+        } else {
+            for (int k = 0; k < chunk; k++) {
+                lbm.increase_ts<Scenario>();
+                lbm.stream();
+                lbm.swap_buffers();
+                lbm.apply_boundaries<Scenario>();
+                lbm.uncorrected_macroscopics();
+                lbm.reset_forces<Scenario>();
+                lbm.ibm_step();
+                lbm.correct_macroscopics();
+                lbm.compute_equilibrium();
+                lbm.collide<Scenario::CollisionOp>();
+            }
+        }
+        t += chunk;
+        lbm.finish_step();                  // the last step of the chunk also stores rho and u (+12 B/node on that step only)
+        cudaEventRecord(stop);
+        cudaEventSynchronize(stop);
+        float ms = 0.0f;
+        cudaEventElapsedTime(&ms, start, stop);
+        gpu_ms += ms;
+        lbm.update_macroscopics();          // device -> host copy of rho, u: outside the timed region, as in the reference's save path
+        if (vtk) lbm.save_vtk(t);
+        if (dump) lbm.save_macroscopics(t);
+        if constexpr (Scenario::has_analytical_solution) {
+            last_error = lbm.compute_error<Scenario>();
+            printf("%s[%d]: error, %.4f%%\n", Scenario::name(), t, last_error);
+        }
+    }
+    const double mass = lbm.total_mass();
+    double sum_rho = 0.0, sum_u2 = 0.0;
+    for (size_t i = 0; i < lbm.h_rho.size(); i++) sum_rho += lbm.h_rho[i];
+    for (size_t i = 0; i < lbm.h_u.size(); i++) sum_u2 += (double)lbm.h_u[i] * lbm.h_u[i];
+    printf("SHIM_RESULT scenario=%s nx=%d ny=%d steps=%d ms_per_step=%.6f mlups=%.3f error_pct=%.6f mass_per_node=%.9f mean_rho=%.9f sum_u2=%.9e\n",
+           Scenario::name(), NX, NY, total_timesteps, gpu_ms / total_timesteps,
+           lbm_b200_mlups((long long)NX * NY, total_timesteps, gpu_ms * 1e-3), last_error, mass / ((double)NX * NY),
+           sum_rho / ((double)NX * NY), sum_u2);
+    return 0;
+}

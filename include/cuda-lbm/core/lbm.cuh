@@ -1,0 +1,431 @@
+// core/lbm.cuh — LBM<2>, the solver object of the reference (src/core/lbm.cuh:33-382), on top of the B200 engine's C ABI.
+//
+// Same public surface and driver protocol as the reference (src/main.cu:72-153):
+//
+//     LBM<dimensions> lbm;  lbm.allocate<Scenario>();  lbm.init<Scenario>();
+//     per step:  increase_ts<S>(); stream(); swap_buffers(); apply_boundaries<S>(); uncorrected_macroscopics();
+//                reset_forces<S>(); ibm_step(); correct_macroscopics(); compute_equilibrium(); collide<S::CollisionOp>();
+//     now and then:  save_vtk(t) / save_macroscopics(t) / update_macroscopics() / compute_error<S>()
+//
+// What differs underneath: the nine per-step methods do not launch nine kernels over three population buffers.  They
+// describe ONE time step, which the engine executes as one fused, register-resident kernel over a single in-place SoA
+// buffer (cuda_lbm_b200/csrc/kernels.cuh).  collide<Op>() closes the description; the step is enqueued when the next one
+// begins (increase_ts) or when its macroscopic fields are asked for — in which case that launch also stores rho and u
+// exactly as the reference's d_rho / d_u hold them after correct_macroscopics().  Work runs on the legacy default stream,
+// so cudaEventRecord(…, 0) pairs around a loop iteration time it as they do for the reference.
+//
+// The scenario's functors run in this translation unit: Init::operator() on the device over whole-grid AoS arrays
+// (rho[node], u[2*node+c], force[2*node+c]) and Boundary::operator() once per node; the results go through
+// lbm_init_fields_device / lbm_set_flags / lbm_set_body_force.  Errors are fatal, as in the reference
+// (src/util/utility.cu:4-12): message to stderr, exit(99).
+#ifndef LBM_H
+#define LBM_H
+
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <filesystem>
+#include <fstream>
+#include <iomanip>
+#include <iostream>
+#include <sstream>
+#include <string>
+#include <type_traits>
+#include <vector>
+
+#include "defines.hpp"
+#include "util/utility.cuh"
+#include "core/lbm_constants.cuh"
+#include "core/streaming/streaming.cuh"
+#include "core/collision/collision.cuh"
+#include "functors/includes.cuh"
+#include "assert.cuh"
+#include "IBM/IBMBody.cuh"
+#include "../../lbm_b200.h"
+
+namespace fs = std::filesystem;
+
+// grid means used by CM<2,OptimalAdapter> in the last step (reference src/core/lbm.cuh:25-29)
+struct MomentInfo {
+    float rho_avg_norm;
+    float j_avg_norm;
+    float pi_avg_norm;
+};
+
+namespace lbm_b200_shim {
+
+inline void fatal(const char* what) {
+    std::fprintf(stderr, "[LBM] %s failed: %s\n", what, lbm_last_error());
+    std::exit(99);
+}
+#define LBM_B200_CALL(expr) do { if ((expr) != LBM_OK) ::lbm_b200_shim::fatal(#expr); } while (0)
+
+// periodic axes: a scenario's own `periodic_x` / `periodic_y` members win over the PERIODIC_X / PERIODIC_Y macros
+template <typename S, typename = void> struct periodic_x_of { static constexpr bool value = lbm_b200_periodic_x_default; };
+template <typename S> struct periodic_x_of<S, std::void_t<decltype(S::periodic_x)>> { static constexpr bool value = S::periodic_x; };
+template <typename S, typename = void> struct periodic_y_of { static constexpr bool value = lbm_b200_periodic_y_default; };
+template <typename S> struct periodic_y_of<S, std::void_t<decltype(S::periodic_y)>> { static constexpr bool value = S::periodic_y; };
+
+// Init functor over the whole grid, one node per thread: init_kernel of src/core/init/init.cuh:29-43 without the population part
+template <typename Init>
+__global__ void init_functor_kernel(Init init, float* rho, float* u, float* force, int n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) init(rho, u, force, (int)i);
+}
+// reset_forces_kernel of src/core/macroscopics/macroscopics.cuh:13-27
+template <typename Init>
+__global__ void force_functor_kernel(Init init, float* rho, float* u, float* force, int n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) init.apply_forces(rho, u, force, (int)i);
+}
+// Boundary functor over the whole grid (setup_boundary_flags, src/core/boundaries/boundaries.cuh:170-197, runs it on the host)
+template <typename Boundary>
+__global__ void boundary_functor_kernel(Boundary b, int* flags, int nx, int ny, int* any_non_fluid) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)nx * ny) return;
+    const int v = b((int)(i % nx), (int)(i / nx));
+    flags[i] = v;
+    if (v != 0) *any_non_fluid = 1;
+}
+// is force[node] the same vector on every node?
+static __global__ void force_uniform_kernel(const float2* force, int n, int* differs) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float2 a = force[0], b = force[i];
+    if (a.x != b.x || a.y != b.y) *differs = 1;
+}
+
+inline int env_int(const char* name, int fallback) {
+    const char* v = std::getenv(name);
+    return v ? std::atoi(v) : fallback;
+}
+
+}  // namespace lbm_b200_shim
+
+template <int dim>
+class LBM {
+    static_assert(dim == 2, "the B200 engine covers the reference's D2Q9 path (LBM<2>)");
+
+private:
+    lbm_handle* h = nullptr;
+    bool step_pending = false;           // a step has been described (collide) but not enqueued yet
+    std::vector<IBMBody> bodies;         // owned from allocate() on, released in free()
+
+    void flush(bool want_macroscopics) {
+        if (!step_pending) return;
+        if (want_macroscopics) LBM_B200_CALL(lbm_step_with_macroscopics(h, 1));
+        else LBM_B200_CALL(lbm_step(h, 1));
+        step_pending = false;
+    }
+
+    template <typename Scenario>
+    void send_consts() {
+        const float nu = Scenario::viscosity;
+        checkCudaErrors(cudaMemcpyToSymbol(vis, &nu, sizeof(float)));
+    }
+
+    template <typename BoundaryFunctor>
+    void setup_boundary_flags(BoundaryFunctor boundary_func) {
+        const long long n = (long long)NX * NY;
+        int *d_flags = nullptr, *d_any = nullptr, any = 0;
+        checkCudaErrors(cudaMalloc(&d_flags, n * sizeof(int)));
+        checkCudaErrors(cudaMalloc(&d_any, sizeof(int)));
+        checkCudaErrors(cudaMemset(d_any, 0, sizeof(int)));
+        lbm_b200_shim::boundary_functor_kernel<<<(unsigned)((n + 255) / 256), 256>>>(boundary_func, d_flags, NX, NY, d_any);
+        checkCudaErrors(cudaGetLastError());
+        checkCudaErrors(cudaMemcpy(&any, d_any, sizeof(int), cudaMemcpyDeviceToHost));
+        if (any) {      // an all-FLUID scenario (Taylor-Green) needs no flag plane at all
+            std::vector<int32_t> flags((size_t)n);
+            checkCudaErrors(cudaMemcpy(flags.data(), d_flags, n * sizeof(int), cudaMemcpyDeviceToHost));
+            LBM_B200_CALL(lbm_set_flags(h, flags.data()));
+        }
+        checkCudaErrors(cudaFree(d_flags));
+        checkCudaErrors(cudaFree(d_any));
+    }
+
+    // Init::apply_forces for every node -> uniform body force (two kernel constants) or a per-node force plane
+    template <typename Init>
+    void upload_forces(Init init, float* d_rho, float* d_u, float* d_force, bool evaluate) {
+        const int n = NX * NY;
+        if (evaluate) {
+            lbm_b200_shim::force_functor_kernel<<<(n + 255) / 256, 256>>>(init, d_rho, d_u, d_force, n);
+            checkCudaErrors(cudaGetLastError());
+        }
+        int* d_differs = nullptr;
+        int differs = 0;
+        checkCudaErrors(cudaMalloc(&d_differs, sizeof(int)));
+        checkCudaErrors(cudaMemset(d_differs, 0, sizeof(int)));
+        lbm_b200_shim::force_uniform_kernel<<<(n + 255) / 256, 256>>>(reinterpret_cast<const float2*>(d_force), n, d_differs);
+        checkCudaErrors(cudaMemcpy(&differs, d_differs, sizeof(int), cudaMemcpyDeviceToHost));
+        checkCudaErrors(cudaFree(d_differs));
+        if (differs) {
+            LBM_B200_CALL(lbm_set_force_field_device(h, d_force));
+        } else {
+            float f0[2];
+            checkCudaErrors(cudaMemcpy(f0, d_force, sizeof(f0), cudaMemcpyDeviceToHost));
+            LBM_B200_CALL(lbm_set_force_field(h, nullptr));
+            LBM_B200_CALL(lbm_set_body_force(h, f0[0], f0[1]));
+        }
+    }
+
+public:
+    std::vector<float> h_rho;            // [node]
+    std::vector<float> h_u;              // [node*2 + c]
+    int timestep = 0, update_ts = 0;
+
+    LBM() = default;
+    LBM(const LBM&) = delete;
+    LBM& operator=(const LBM&) = delete;
+
+    // LBM::allocate<Scenario>() — src/core/lbm.cuh:92-125
+    template <typename Scenario>
+    void allocate() {
+        std::cout << "[LBM]: allocating\n";
+        h_rho.resize((size_t)NX * NY);
+        h_u.resize((size_t)NX * NY * dimensions);
+
+        lbm_config cfg;
+        LBM_B200_CALL(lbm_default_config(&cfg));
+        cfg.nx = NX;
+        cfg.ny = NY;
+        cfg.periodic_x = lbm_b200_shim::periodic_x_of<Scenario>::value;
+        cfg.periodic_y = lbm_b200_shim::periodic_y_of<Scenario>::value;
+        cfg.collision = Scenario::CollisionOp::lbm_b200_op;
+        cfg.viscosity = Scenario::viscosity;
+        for (int i = 0; i < quadratures; i++) cfg.S[i] = Scenario::S[i];
+        cfg.u_max = Scenario::u_max;
+        // LBM_QK_REFERENCE reproduces the reference's arithmetic including its defects; 0 repairs them
+        cfg.quirks = lbm_b200_shim::env_int("LBM_B200_QUIRKS", LBM_QK_REFERENCE);
+        cfg.adapter_mode = lbm_b200_shim::env_int("LBM_B200_ADAPTER", LBM_ADAPTER_EXACT);
+        int dev = 0;
+        checkCudaErrors(cudaGetDevice(&dev));
+        cfg.device = dev;
+        LBM_B200_CALL(lbm_create(&cfg, &h));
+        LBM_B200_CALL(lbm_set_stream(h, (void*)cudaStreamLegacy));
+
+        Scenario::add_bodies();
+        for (const IBMBody& b : Scenario::IBM_bodies) {
+            LBM_B200_CALL(lbm_add_body(h, b.points, b.num_points));
+            bodies.push_back(b);
+        }
+    }
+
+    void free() {
+        if (!h) return;
+        std::cout << "[LBM]: Freeing\n";
+        step_pending = false;
+        LBM_B200_CALL(lbm_destroy(h));
+        h = nullptr;
+        for (IBMBody& b : bodies) h_ibm_free(b);
+        bodies.clear();
+    }
+
+    // LBM::init<Scenario>() — src/core/init/init.cuh:45-86
+    template <typename Scenario>
+    void init() {
+        LBM_DEVICE_ASSERT(Scenario::viscosity > 0.0f, "Negative Viscosity");
+        LBM_DEVICE_ASSERT(Scenario::tau > 0.5f, "Instability warning: tau < 0.5");
+        LBM_DEVICE_ASSERT(Scenario::u_max < 0.5f, "Instability warning: u_max > 0.5");
+        auto init = Scenario::init();
+        auto boundary_func = Scenario::boundary();
+        send_consts<Scenario>();
+
+        const int n = NX * NY;
+        float *d_rho = nullptr, *d_u = nullptr, *d_force = nullptr;
+        checkCudaErrors(cudaMalloc(&d_rho, (size_t)n * sizeof(float)));
+        checkCudaErrors(cudaMalloc(&d_u, (size_t)n * 2 * sizeof(float)));
+        checkCudaErrors(cudaMalloc(&d_force, (size_t)n * 2 * sizeof(float)));
+        // entries a functor leaves unwritten are zero here (the reference reads uninitialised memory, Appendix A-D13)
+        checkCudaErrors(cudaMemset(d_rho, 0, (size_t)n * sizeof(float)));
+        checkCudaErrors(cudaMemset(d_u, 0, (size_t)n * 2 * sizeof(float)));
+        checkCudaErrors(cudaMemset(d_force, 0, (size_t)n * 2 * sizeof(float)));
+        lbm_b200_shim::init_functor_kernel<<<(n + 255) / 256, 256>>>(init, d_rho, d_u, d_force, n);
+        checkCudaErrors(cudaGetLastError());
+        checkCudaErrors(cudaDeviceSynchronize());
+
+        setup_boundary_flags(boundary_func);
+        upload_forces(init, d_rho, d_u, d_force, true);     // what reset_forces<Scenario>() computes every step in the reference
+        LBM_B200_CALL(lbm_init_fields_device(h, d_rho, d_u));
+        LBM_B200_CALL(lbm_sync(h));
+        checkCudaErrors(cudaFree(d_rho));
+        checkCudaErrors(cudaFree(d_u));
+        checkCudaErrors(cudaFree(d_force));
+        timestep = 0;
+        update_ts = 0;
+        step_pending = false;
+        printf("[init_kernel]: Threads executed: %d\n", n);
+    }
+
+    template <typename Scenario>
+    void increase_ts() {
+        flush(false);
+        timestep++;
+        Scenario::update_ts(timestep);
+    }
+
+    // ---- the reference's per-kernel host methods (src/core/lbm.cuh:345-377): one fused launch stands for all of them
+    void stream() {}
+    void swap_buffers() {}
+    template <typename Scenario> void apply_boundaries() {}
+    void uncorrected_macroscopics() {}
+    // Init::apply_forces was evaluated in init(); a scenario whose force changes in time calls refresh_forces<S>() instead
+    template <typename Scenario> void reset_forces() {}
+    void ibm_step() {}
+    void correct_macroscopics() {}
+    void compute_equilibrium() {}
+    void compute_forces() {}
+    template <typename CollisionOp>
+    void collide() {
+        if (h == nullptr) { std::fprintf(stderr, "[LBM] collide() before allocate()\n"); std::exit(99); }
+        flush(false);                    // a driver that never calls increase_ts still advances one step per collide()
+        step_pending = true;
+    }
+
+    // extension: n whole time steps without per-step host calls (timestep and Scenario::t advance by n)
+    template <typename Scenario>
+    void run(int n) {
+        if (n <= 0) return;
+        flush(false);
+        LBM_B200_CALL(lbm_step(h, n - 1));
+        timestep += n;
+        Scenario::update_ts(timestep);
+        step_pending = true;
+    }
+
+    // extension: enqueue the step described so far now (instead of at the next increase_ts), keeping its rho / u for a
+    // following update_macroscopics() — lets a driver bracket exactly the stepping work with CUDA events
+    void finish_step(bool keep_macroscopics = true) { flush(keep_macroscopics); }
+
+    // extension: re-evaluate Init::apply_forces with the macroscopic fields of the last update_macroscopics()
+    template <typename Scenario>
+    void refresh_forces() {
+        flush(false);
+        const int n = NX * NY;
+        float *d_rho = nullptr, *d_u = nullptr, *d_force = nullptr;
+        checkCudaErrors(cudaMalloc(&d_rho, (size_t)n * sizeof(float)));
+        checkCudaErrors(cudaMalloc(&d_u, (size_t)n * 2 * sizeof(float)));
+        checkCudaErrors(cudaMalloc(&d_force, (size_t)n * 2 * sizeof(float)));
+        checkCudaErrors(cudaMemcpy(d_rho, h_rho.data(), (size_t)n * sizeof(float), cudaMemcpyHostToDevice));
+        checkCudaErrors(cudaMemcpy(d_u, h_u.data(), (size_t)n * 2 * sizeof(float), cudaMemcpyHostToDevice));
+        checkCudaErrors(cudaMemset(d_force, 0, (size_t)n * 2 * sizeof(float)));
+        upload_forces(Scenario::init(), d_rho, d_u, d_force, true);
+        checkCudaErrors(cudaFree(d_rho));
+        checkCudaErrors(cudaFree(d_u));
+        checkCudaErrors(cudaFree(d_force));
+    }
+
+    // LBM::update_macroscopics() — src/core/lbm.cuh:148-154
+    void update_macroscopics() {
+        flush(true);        // no-op after finish_step(): the macroscopics of the current step are already on the device
+        update_ts = timestep;
+        LBM_B200_CALL(lbm_get_macroscopics(h, h_rho.data(), h_u.data()));
+    }
+
+    // device views of rho[node] and u[node*2+c], valid until the next step (d_rho / d_u of the reference)
+    float* get_rho() {
+        flush(true);
+        const float *r = nullptr, *u = nullptr;
+        LBM_B200_CALL(lbm_get_macroscopics_device(h, &r, &u));
+        return const_cast<float*>(r);
+    }
+    float* get_u() {
+        flush(true);
+        const float *r = nullptr, *u = nullptr;
+        LBM_B200_CALL(lbm_get_macroscopics_device(h, &r, &u));
+        return const_cast<float*>(u);
+    }
+
+    // LBM::compute_error<Scenario>() — src/core/lbm.cuh:163-171
+    template <typename Scenario>
+    float compute_error() {
+        if constexpr (Scenario::has_analytical_solution) {
+            return Scenario::compute_error(*this);
+        } else {
+            printf("Scenario does not provide verification/validation.\n");
+            return 0.0f;
+        }
+    }
+
+    // grid means of rho, rho|u|, |Pi| that the last CM<2,OptimalAdapter> step used (the reference's d_moment_avg)
+    MomentInfo moment_avg() {
+        flush(false);
+        float a[3];
+        LBM_B200_CALL(lbm_moment_avg(h, a));
+        return MomentInfo{a[0], a[1], a[2]};
+    }
+    double total_mass() {
+        flush(false);
+        double m = 0.0;
+        LBM_B200_CALL(lbm_total_mass(h, &m));
+        return m;
+    }
+    void synchronize() {
+        flush(false);
+        LBM_B200_CALL(lbm_sync(h));
+    }
+    lbm_handle* handle() { return h; }
+
+    // raw dumps read by src/graphics/*.py: output/density/density_<t>.bin (NX*NY floats) and
+    // output/velocity/velocity_<t>.bin (NX*NY*2 floats, AoS) — src/core/lbm.cuh:173-204
+    void save_macroscopics(int ts) {
+        update_macroscopics();
+        const struct { const char* dir; const char* stem; const std::vector<float>* data; } outs[2] = {
+            {"output/density", "density_", &h_rho}, {"output/velocity", "velocity_", &h_u}};
+        for (const auto& o : outs) {
+            std::error_code ec;
+            fs::create_directories(o.dir, ec);
+            const std::string path = std::string(o.dir) + "/" + o.stem + std::to_string(ts) + ".bin";
+            std::ofstream f(path, std::ios::binary);
+            if (!f) { printf("Error: Could not open file %s for writing.\n", path.c_str()); return; }
+            f.write(reinterpret_cast<const char*>(o.data->data()), (std::streamsize)(o.data->size() * sizeof(float)));
+        }
+    }
+
+    // VTK ImageData with raw appended data, same arrays and names as the reference writes (src/core/lbm.cuh:262-343):
+    // Float32 "Density", then Float32 x3 "Velocity" with a zero z component; UInt64 block headers.
+    void save_vtk(int ts) {
+        update_macroscopics();
+        const std::string dir = "output/vtk";
+        std::error_code ec;
+        fs::create_directories(dir, ec);
+        if (ec) { std::cerr << "Filesystem error creating directory " << dir << ": " << ec.message() << std::endl; return; }
+        std::ostringstream name;
+        name << dir << "/sim_data_" << std::setw(6) << std::setfill('0') << ts << ".vti";
+        std::ofstream out(name.str(), std::ios::binary);
+        if (!out) { std::cerr << "Error: Could not open file " << name.str() << " for writing." << std::endl; return; }
+        std::cout << "[VTK Export] Saving data for timestep " << ts << " to " << name.str() << std::endl;
+        const uint64_t rho_bytes = h_rho.size() * sizeof(float);
+        const std::string extent = "0 " + std::to_string(NX - 1) + " 0 " + std::to_string(NY - 1) + " 0 " + std::to_string(NZ - 1);
+        out << "<?xml version=\"1.0\"?>\n"
+            << "<VTKFile type=\"ImageData\" version=\"1.0\" byte_order=\"LittleEndian\" header_type=\"UInt64\">\n"
+            << "  <ImageData WholeExtent=\"" << extent << "\" Origin=\"0 0 0\" Spacing=\"1 1 1\">\n"
+            << "    <Piece Extent=\"" << extent << "\">\n"
+            << "      <PointData Scalars=\"Density\" Vectors=\"Velocity\">\n"
+            << "        <DataArray type=\"Float32\" Name=\"Density\" format=\"appended\" offset=\"0\"/>\n"
+            << "        <DataArray type=\"Float32\" Name=\"Velocity\" NumberOfComponents=\"3\" format=\"appended\" offset=\"" << rho_bytes << "\"/>\n"
+            << "      </PointData>\n"
+            << "      <CellData>\n"
+            << "      </CellData>\n"
+            << "    </Piece>\n"
+            << "  </ImageData>\n"
+            << "  <AppendedData encoding=\"raw\">\n"
+            << "   _";
+        std::vector<float> u3((size_t)NX * NY * 3);
+        for (size_t node = 0; node < (size_t)NX * NY; node++) {
+            u3[3 * node] = h_u[2 * node];
+            u3[3 * node + 1] = h_u[2 * node + 1];
+            u3[3 * node + 2] = 0.0f;
+        }
+        const uint64_t u_bytes = u3.size() * sizeof(float);
+        out.write(reinterpret_cast<const char*>(&rho_bytes), sizeof(uint64_t));
+        out.write(reinterpret_cast<const char*>(h_rho.data()), (std::streamsize)rho_bytes);
+        out.write(reinterpret_cast<const char*>(&u_bytes), sizeof(uint64_t));
+        out.write(reinterpret_cast<const char*>(u3.data()), (std::streamsize)u_bytes);
+        out << "\n  </AppendedData>\n</VTKFile>\n";
+    }
+
+    ~LBM() { free(); }
+};
+
+#endif  // LBM_H

@@ -116,6 +116,10 @@ struct Scenario : public ScenarioTrait<PoiseuilleInit, PoiseuilleBoundary, Poise
     static InitType init() { return InitType(u_max); }
     static BoundaryType boundary() { return BoundaryType(); }
     static ValidationType validation() { return ValidationType(u_max, viscosity); }
+#ifdef REF_POIS_BODY
+    // the immersed cylinder the reference's own Poiseuille scenario adds (poiseuilleScenario.cuh:46-53)
+    static void add_bodies() { IBM_bodies.push_back(create_cylinder(48.0f, NY / 2.0f, 8.0f)); }
+#endif
 };
 #elif REF_CASE == 2 || REF_CASE == 3
 #ifndef REF_UMAX
