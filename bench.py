@@ -209,6 +209,9 @@ def main():
     kern_ms = ms / args.steps
     achieved = BYTES_PER_UPDATE * nloc / (kern_ms * 1e-3) / 1e9
     peak, peak_src = measured_peak()
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of this very command
+    # (profiles/r01_ncu_bench_kernel.md: 77.355 GB odd phase, 77.259 GB even phase); other sizes were not captured
+    traffic = 77.307e9 * (nloc / float(NX * NY)) if (nx == NX and args.collision == "BGK") else None
 
     # ---------------- end to end through the public API with host buffers ----------------
     e2e = None
@@ -254,7 +257,8 @@ def main():
                            "l2_policy": f"populations per GPU {36.0 * nloc / 1e9:.1f} GB >> 126 MB L2 (no flush needed)"},
                 "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": None, "peak_source": peak_src, "kernel": "lbm::step_kernel (fused pull+collide+push)",
+                             "traffic": traffic, "traffic_source": "ncu dram bytes per launch, mean of the odd/even phase captures (profiles/r01_ncu_bench_kernel.md)",
+                             "peak_source": peak_src, "kernel": "lbm::step_vec_kernel<BGK, odd|even> (fused pull + collide + push, 4 cells/thread)",
                              "algorithmic_bytes_per_launch": BYTES_PER_UPDATE * nloc, "kernel_ms": kern_ms},
                 "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
