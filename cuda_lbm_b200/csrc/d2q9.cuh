@@ -15,13 +15,9 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include "collide.cuh"
 
 namespace lbm {
-
-constexpr int Q = 9;
-
-// quirk bits (include/lbm_b200.h)
-constexpr int QK_D1 = 1, QK_D2 = 2, QK_D3 = 4, QK_D7 = 8, QK_D8 = 16, QK_D11 = 32;
 
 // BC_flag values — reference src/core/lbm_constants.cuh:377-397
 enum : int {
@@ -31,13 +27,6 @@ enum : int {
 };
 constexpr uint8_t FLAG_IBM = 0x80;   // node lies in a marker stencil: force comes from ibm_force[]
 constexpr uint8_t FLAG_MASK = 0x1f;
-
-// lattice tables — reference src/core/lbm_constants.cuh:13-31 (h_C, h_OPP, h_weights)
-__host__ __device__ __forceinline__ constexpr int cx(int q) { return (q == 1 || q == 5 || q == 8) ? 1 : ((q == 3 || q == 6 || q == 7) ? -1 : 0); }
-__host__ __device__ __forceinline__ constexpr int cy(int q) { return (q == 2 || q == 5 || q == 6) ? 1 : ((q == 4 || q == 7 || q == 8) ? -1 : 0); }
-__host__ __device__ __forceinline__ constexpr int opp(int q) { return q == 0 ? 0 : (q <= 4 ? ((q + 1) % 4) + 1 : ((q - 3) % 4) + 5); }
-__host__ __device__ __forceinline__ constexpr float wq(int q) { return q == 0 ? 4.0f / 9.0f : (q <= 4 ? 1.0f / 9.0f : 1.0f / 36.0f); }
-static_assert(opp(1) == 3 && opp(2) == 4 && opp(3) == 1 && opp(4) == 2 && opp(5) == 7 && opp(6) == 8 && opp(7) == 5 && opp(8) == 6, "OPP");
 
 struct Params {
     float* A[Q];            // slot planes, each (ny_local+2) rows of nx floats; row 0 / ny_local+1 are ghost rows
@@ -173,22 +162,14 @@ __device__ __forceinline__ float feq(int q, float rho, float ux, float uy, float
 
 struct Moments { float rho, inv_rho, ux, uy, pxx, pxy, pyy; };
 
-// uncorrected_macroscopics_kernel<2> — reference src/core/macroscopics/macroscopics.cu:5-38
+// uncorrected_macroscopics_kernel<2> — reference src/core/macroscopics/macroscopics.cu:5-38 (scalar view of moments_v, collide.cuh)
 __device__ __forceinline__ Moments moments(const float g[Q]) {
-    Moments m;
-    m.rho = g[0] + g[1] + g[2] + g[3] + g[4] + g[5] + g[6] + g[7] + g[8];
-    float jx = (g[1] - g[3]) + (g[5] - g[6]) + (g[8] - g[7]);
-    float jy = (g[2] - g[4]) + (g[5] - g[8]) + (g[6] - g[7]);
-    float inv = 1.0f / m.rho;
-    m.inv_rho = inv;
-    m.ux = jx * inv; m.uy = jy * inv;
-    float d = g[5] + g[6] + g[7] + g[8];
-    m.pxx = g[1] + g[3] + d;
-    m.pyy = g[2] + g[4] + d;
-    m.pxy = (g[5] - g[6]) + (g[7] - g[8]);
-    return m;
+    V1 v[Q];
+#pragma unroll
+    for (int q = 0; q < Q; q++) v[q].a = g[q];
+    const Mom<V1> m = moments_v(v);
+    return Moments{m.rho.a, m.inv_rho.a, m.ux.a, m.uy.a, m.pxx.a, m.pxy.a, m.pyy.a};
 }
-__device__ __forceinline__ float pi_norm(const Moments& m) { return sqrtf(m.pxx * m.pxx + 2.0f * m.pxy * m.pxy + m.pyy * m.pyy); }
 
 // ------------------------------------------------------------------ boundary functors (Appendix D step 2)
 __device__ __forceinline__ int find_sorted(const long long* a, int n, long long key) {
@@ -355,139 +336,17 @@ __device__ __forceinline__ void apply_bc(const Params& p, int flag, float g[Q], 
     }
 }
 
-// ------------------------------------------------------------------ collision operators (Appendix D step 7)
-// BGK<2>::apply — reference src/core/collision/BGK/BGK.cuh:13-51 (Guo forcing)
-__device__ __forceinline__ void collide_bgk(const Params& p, float g[Q], float rho, float ux, float uy, float Fx, float Fy) {
-    const float om = p.omega, k = 1.0f - 0.5f * om;
-    const float usq15 = 1.5f * (ux * ux + uy * uy);
-    const float uF = ux * Fx + uy * Fy;
+// collision operators: collide.cuh
+__device__ __forceinline__ Relax relax_of(const Params& p) {
+    Relax r;
+    r.omega = p.omega;
 #pragma unroll
-    for (int q = 0; q < Q; q++) {
-        float cu = cx(q) * ux + cy(q) * uy;
-        float cF = cx(q) * Fx + cy(q) * Fy;
-        float fe = wq(q) * rho * (1.0f + 3.0f * cu + 4.5f * cu * cu - usq15);
-        float ft = (wq(q) * k) * (3.0f * (cF - uF) + 9.0f * cu * cF);
-        g[q] = g[q] - om * (g[q] - fe) + ft;
-    }
+    for (int i = 0; i < Q; i++) r.S[i] = p.S[i];
+    r.quirks = p.quirks;
+    return r;
 }
-
-// MRT<2>::apply + compute_forcing_term — reference src/core/collision/MRT/MRT.cu:4-76, M / M^-1 of
-// lbm_constants.cuh:33-55 folded into add/sub chains; m_eq = M f_eq(rho,u) written in closed form.
-__device__ __forceinline__ void collide_mrt(const Params& p, float g[Q], float rho, float ux, float uy, float Fx, float Fy) {
-    const float sA = (g[1] + g[3]) + (g[2] + g[4]), sD = (g[5] + g[7]) + (g[6] + g[8]);
-    float m[Q];
-    m[0] = g[0] + sA + sD;
-    m[1] = -4.0f * g[0] - sA + 2.0f * sD;
-    m[2] = 4.0f * g[0] - 2.0f * sA + sD;
-    const float dx1 = g[1] - g[3], dx2 = (g[5] - g[6]) + (g[8] - g[7]);
-    const float dy1 = g[2] - g[4], dy2 = (g[5] - g[8]) + (g[6] - g[7]);
-    m[3] = dx1 + dx2;
-    m[4] = -2.0f * dx1 + dx2;
-    m[5] = dy1 + dy2;
-    m[6] = -2.0f * dy1 + dy2;
-    m[7] = (g[1] + g[3]) - (g[2] + g[4]);
-    m[8] = (g[5] + g[7]) - (g[6] + g[8]);
-    const float jx = rho * ux, jy = rho * uy, usq = ux * ux + uy * uy;
-    float me[Q] = {rho, rho * (3.0f * usq - 2.0f), rho * (1.0f - 3.0f * usq), jx, -jx, jy, -jy, rho * (ux * ux - uy * uy), rho * ux * uy};
-    const float uF = Fx * ux + Fy * uy;
-    float F[Q];
-    F[0] = 0.0f; F[1] = 6.0f * uF; F[2] = -6.0f * uF; F[3] = Fx;
-    if (p.quirks & QK_D2) { F[4] = Fy; F[5] = -Fx; } else { F[4] = -Fx; F[5] = Fy; }
-    F[6] = -Fy; F[7] = 2.0f * (Fx * ux - Fy * uy); F[8] = Fx * uy + Fy * ux;
-#pragma unroll
-    for (int k = 0; k < Q; k++) m[k] = m[k] - p.S[k] * (m[k] - me[k]) + (1.0f - 0.5f * p.S[k]) * F[k];
-    const float a = m[0] * (1.0f / 9.0f);
-    const float b1 = m[1] * (1.0f / 36.0f), b2 = m[2] * (1.0f / 36.0f);
-    const float ax = a - b1 - 2.0f * b2, dg = a + 2.0f * b1 + b2;
-    const float x6 = (m[3] - m[4]) * (1.0f / 6.0f), y6 = (m[5] - m[6]) * (1.0f / 6.0f);
-    const float xd = m[3] * (1.0f / 6.0f) + m[4] * (1.0f / 12.0f), yd = m[5] * (1.0f / 6.0f) + m[6] * (1.0f / 12.0f);
-    const float p4 = m[7] * 0.25f, q4 = m[8] * 0.25f;
-    g[0] = a - 4.0f * b1 + 4.0f * b2;
-    g[1] = ax + x6 + p4;
-    g[2] = ax + y6 - p4;
-    g[3] = ax - x6 + p4;
-    g[4] = ax - y6 - p4;
-    g[5] = dg + xd + yd + q4;
-    g[6] = dg - xd + yd - q4;
-    g[7] = dg - xd - yd + q4;
-    g[8] = dg + xd - yd - q4;
-}
-
-// OptimalAdapter::compute_higher_order_relaxation — reference src/core/collision/adapters.cuh:48-111
-// The three grid means are the same for every cell of a step, so the divisions become multiplications by reciprocals
-// taken once per thread (<= 1 ulp on a ratio that enters tau* with a weight of 1e-2 .. 1e-4).
-struct AdapterAvg { float inv_rho, inv_j, inv_pi; };
 __device__ __forceinline__ AdapterAvg load_adapter_avg(const float* avg) {
     AdapterAvg a; a.inv_rho = 1.0f / avg[0]; a.inv_j = 1.0f / avg[1]; a.inv_pi = 1.0f / avg[2]; return a;
-}
-__device__ __forceinline__ float optimal_rate(float rho, float jmag, float pimag, const AdapterAvg& a) {
-    float ts = 0.0003f * (rho * a.inv_rho) - 0.00775f * (jmag * a.inv_j) + 0.00016f * (pimag * a.inv_pi) + 0.0087f;
-    ts = ts > 0.0f ? ts : 0.005f;
-    ts = fminf(ts, 1.5f);
-    return 1.0f / (3.0f * ts + 0.5f);
-}
-
-// CM<2,Adapter>::apply — reference src/core/collision/CM/CM.cuh:27-139.  The reference accumulates the
-// nine central moments with per-direction polynomials and multiplies by an 81-entry T^-1(u)
-// (cm_matrix_inverse, :141-250, ~900 flop).  Here: raw moments (add chains) -> binomial shift by -u ->
-// relax -> shift by +u -> populations; algebraically identical (tests/test_transforms.py), ~200 flop.
-// jmag = rho |u| and pimag = |Pi| of the cell (only read when OPTIMAL): the same values that enter the grid means.
-template <bool OPTIMAL>
-__device__ __forceinline__ void collide_cm(const Params& p, float g[Q], float ux, float uy, float Fx, float Fy,
-                                           float jmag = 0.f, float pimag = 0.f, const AdapterAvg* avg = nullptr) {
-    // raw moments m_ab = sum f cx^a cy^b
-    const float d = (g[5] + g[7]) + (g[6] + g[8]);
-    const float m00 = g[0] + ((g[1] + g[3]) + (g[2] + g[4])) + d;      // rho recomputed from f (:38-41)
-    const float m10 = (g[1] - g[3]) + ((g[5] - g[6]) + (g[8] - g[7]));
-    const float m01 = (g[2] - g[4]) + ((g[5] - g[8]) + (g[6] - g[7]));
-    const float m20 = (g[1] + g[3]) + d, m02 = (g[2] + g[4]) + d;
-    const float m11 = (g[5] + g[7]) - (g[6] + g[8]);
-    const float m21 = (g[5] + g[6]) - (g[7] + g[8]);       // sum f cx^2 cy
-    const float m12 = (g[5] + g[8]) - (g[6] + g[7]);       // sum f cx cy^2
-    const float m22 = d;
-    const float rho = m00;
-    const float ux2 = ux * ux, uy2 = uy * uy, uxuy = ux * uy;
-    // central moments about u
-    const float k10 = m10 - ux * m00, k01 = m01 - uy * m00;
-    const float k20 = m20 - 2.0f * ux * m10 + ux2 * m00;
-    const float k02 = m02 - 2.0f * uy * m01 + uy2 * m00;
-    const float k11 = m11 - ux * m01 - uy * m10 + uxuy * m00;
-    const float a21 = m21 - 2.0f * ux * m11 + ux2 * m01;            // sum f (cx-ux)^2 cy
-    const float a12 = m12 - 2.0f * uy * m11 + uy2 * m10;            // sum f cx (cy-uy)^2
-    const float k21 = a21 - uy * k20, k12 = a12 - ux * k02;
-    const float k22 = m22 - 2.0f * uy * m21 + uy2 * m20 - 2.0f * ux * a12 + ux2 * k02;
-    const float cs2 = 1.0f / 3.0f;
-    float k[Q] = {m00, k10, k01, k20 + k02, k20 - k02, k11, k21, k12, k22};
-    const float keq[Q] = {rho, 0.0f, 0.0f, 2.0f * rho * cs2, 0.0f, 0.0f, 0.0f, 0.0f, rho * cs2 * cs2};
-    const float F[Q] = {0.0f, Fx, Fy, 0.0f, 0.0f, 0.0f, Fy * cs2, Fx * cs2, 0.0f};
-    float hi = 1.0f;
-    if (OPTIMAL) hi = optimal_rate(rho, jmag, pimag, *avg);
-#pragma unroll
-    for (int i = 0; i < Q; i++) {
-        float r = (OPTIMAL && i > 5) ? hi : p.S[i];                // AdapterBase::is_higher_order, adapters.cuh:8-13
-        k[i] = k[i] - r * (k[i] - keq[i]) + (1.0f - 0.5f * r) * F[i];
-    }
-    // back to raw moments (shift by +u)
-    const float c00 = k[0], c10 = k[1], c01 = k[2];
-    const float c20 = 0.5f * (k[3] + k[4]), c02 = 0.5f * (k[3] - k[4]);
-    const float c11 = k[5], c21 = k[6], c12 = k[7], c22 = k[8];
-    const float r10 = c10 + ux * c00, r01 = c01 + uy * c00;
-    const float r20 = c20 + 2.0f * ux * c10 + ux2 * c00;
-    const float r02 = c02 + 2.0f * uy * c01 + uy2 * c00;
-    const float r11 = c11 + ux * c01 + uy * c10 + uxuy * c00;
-    const float b12 = c12 + 2.0f * uy * c11 + uy2 * c10;            // sum f (cx-ux)(cy)^2
-    const float r21 = c21 + 2.0f * ux * c11 + ux2 * c01 + uy * r20;
-    const float r12 = b12 + ux * r02;
-    const float r22 = c22 + 2.0f * uy * c21 + uy2 * c20 + 2.0f * ux * b12 + ux2 * r02;
-    g[0] = c00 - r20 - r02 + r22;
-    g[1] = 0.5f * ((r10 + r20) - (r12 + r22));
-    g[3] = 0.5f * ((r20 - r10) + (r12 - r22));
-    g[2] = 0.5f * ((r01 + r02) - (r21 + r22));
-    g[4] = 0.5f * ((r02 - r01) + (r21 - r22));
-    g[5] = 0.25f * ((r11 + r22) + (r21 + r12));
-    g[6] = 0.25f * ((r22 - r11) + (r21 - r12));
-    g[7] = 0.25f * ((r11 + r22) - (r21 + r12));
-    g[8] = 0.25f * ((r22 - r11) - (r21 - r12));
 }
 
 }  // namespace lbm

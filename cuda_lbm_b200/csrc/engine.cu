@@ -571,13 +571,33 @@ static int pre_passes(lbm_handle* h, int t, bool want_moments) {
         h->pre_for_ts = t;
     }
     if (want_moments) {
-        dim3 g = grid_of(h);
-        const long long nb = (long long)g.x * g.y;
-        int rc = ensure_partials(h, nb); if (rc) return rc;
-        Params pm = p; pm.partials = h->partials;
-        if (odd) moments_kernel<true><<<g, BX, 0, h->stream>>>(pm); else moments_kernel<false><<<g, BX, 0, h->stream>>>(pm);
-        h->launches++;
-        reduce_partials(h, nb);
+        long long nparts;
+        if (!use_vec(h)) {
+            dim3 g = grid_of(h);
+            nparts = (long long)g.x * g.y;
+            int rc = ensure_partials(h, nparts); if (rc) return rc;
+            Params pm = p; pm.partials = h->partials;
+            if (odd) moments_kernel<true><<<g, BX, 0, h->stream>>>(pm); else moments_kernel<false><<<g, BX, 0, h->stream>>>(pm);
+            h->launches++;
+        } else {
+            const bool general = is_general(h);
+            if (general) { int rc = ensure_segments(h); if (rc) return rc; }
+            const int ngen = general ? h->gen_count : 0;
+            int threads; dim3 gv = vec_grid(h, threads);
+            const long long nvb = (long long)gv.x * gv.y;
+            nparts = nvb + ngen;
+            int rc = ensure_partials(h, nparts); if (rc) return rc;
+            Params pm = p; pm.partials = h->partials;
+            if (general) pm.segmask = h->segmask;
+            if (odd) moments_vec_kernel<true><<<gv, threads, 0, h->stream>>>(pm); else moments_vec_kernel<false><<<gv, threads, 0, h->stream>>>(pm);
+            h->launches++;
+            if (ngen > 0) {
+                Params pg = p; pg.gen_list = h->gen_list; pg.partials = h->partials + 3 * nvb;
+                if (odd) moments_kernel<true><<<dim3(ngen, 1), BX, 0, h->stream>>>(pg); else moments_kernel<false><<<dim3(ngen, 1), BX, 0, h->stream>>>(pg);
+                h->launches++;
+            }
+        }
+        reduce_partials(h, nparts);
         if (h->cfg.world == 1) h->avg_for_ts = t;
     }
     return LBM_OK;

@@ -32,8 +32,10 @@ __device__ __forceinline__ void node_pre_collision(const Params& p, int x, int y
         }
     }
     // correct_macroscopics_kernel<2> (macroscopics.cu:99-110): u += F / (2 rho)
-    const float h = 0.5f * s.m.inv_rho;               // == 0.5f / rho bit for bit (scaling by a power of two)
-    s.ux = s.m.ux + s.Fx * h; s.uy = s.m.uy + s.Fy * h;
+    // (0.5f * inv_rho == 0.5f / rho bit for bit: scaling by a power of two; same FMA form as the vector kernel)
+    const float h = __fmul_rn(s.m.inv_rho, 0.5f);
+    s.ux = s.m.ux; s.uy = s.m.uy;
+    if (s.Fx != 0.0f || s.Fy != 0.0f) { s.ux = __fmaf_rn(s.Fx, h, s.m.ux); s.uy = __fmaf_rn(s.Fy, h, s.m.uy); }
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -52,7 +54,8 @@ __device__ __forceinline__ void block_partials(float a, float b, float c, float*
     if (threadIdx.x == 0) {
         float s0 = 0.f, s1 = 0.f, s2 = 0.f;
 #pragma unroll
-        for (int i = 0; i < BX / 32; i++) { s0 += sm[0][i]; s1 += sm[1][i]; s2 += sm[2][i]; }
+        for (int i = 0; i < BX / 32; i++)
+            if (i < (int)((blockDim.x + 31) >> 5)) { s0 += sm[0][i]; s1 += sm[1][i]; s2 += sm[2][i]; }      // the vector kernel may run narrower blocks
         out[0] = s0; out[1] = s1; out[2] = s2;
     }
 }
@@ -81,11 +84,23 @@ __global__ void __launch_bounds__(BX) step_kernel(const Params p) {
             p.rho_out[ln] = s.m.rho;
             p.u_out[ln] = make_float2(s.ux, s.uy);
         }
-        if (COLL == C_CMOPT) { s0 = s.m.rho; s1 = sqrtf(s.ux * s.ux + s.uy * s.uy) * s.m.rho; s2 = pi_norm(s.m); }
-        if (COLL == C_BGK) collide_bgk(p, s.g, s.m.rho, s.ux, s.uy, s.Fx, s.Fy);
-        else if (COLL == C_MRT) collide_mrt(p, s.g, s.m.rho, s.ux, s.uy, s.Fx, s.Fy);
-        else if (COLL == C_CM) collide_cm<false>(p, s.g, s.ux, s.uy, s.Fx, s.Fy);
-        else { const AdapterAvg av = load_adapter_avg(p.avg); collide_cm<true>(p, s.g, s.ux, s.uy, s.Fx, s.Fy, s1, s2, &av); }
+        V1 gv[Q];
+#pragma unroll
+        for (int q = 0; q < Q; q++) gv[q].a = s.g[q];
+        const V1 rho{s.m.rho}, ux{s.ux}, uy{s.uy}, Fx{s.Fx}, Fy{s.Fy};
+        const bool forced = s.Fx != 0.0f || s.Fy != 0.0f;
+        const Relax rx = relax_of(p);
+        if (COLL == C_BGK) collide_bgk_v(rx, gv, rho, ux, uy, forced, Fx, Fy);
+        else if (COLL == C_MRT) collide_mrt_v(rx, gv, rho, ux, uy, forced, Fx, Fy);
+        else if (COLL == C_CM) collide_cm_v<false>(rx, gv, ux, uy, forced, Fx, Fy, V1{1.0f});
+        else {
+            const V1 jm = jmag_v(ux, uy, rho), pm = pi_norm_v(Mom<V1>{rho, V1{s.m.inv_rho}, V1{s.m.ux}, V1{s.m.uy}, V1{s.m.pxx}, V1{s.m.pxy}, V1{s.m.pyy}});
+            s0 = s.m.rho; s1 = jm.a; s2 = pm.a;
+            const AdapterAvg av = load_adapter_avg(p.avg);
+            collide_cm_v<true>(rx, gv, ux, uy, forced, Fx, Fy, optimal_rate_v(rho, jm, pm, av));
+        }
+#pragma unroll
+        for (int q = 0; q < Q; q++) s.g[q] = gv[q].a;
         push<ODD>(p, x, yl, s.e, s.g);
     }
     if (COLL == C_CMOPT && p.partials) block_partials(s0, s1, s2, p.partials + 3 * ((long long)blockIdx.y * gridDim.x + blockIdx.x));
@@ -105,11 +120,45 @@ constexpr unsigned FULL = 0xffffffffu;
 #define LBM_VEC_MIN_BLOCKS_EVEN 6
 #endif
 #ifndef LBM_VEC_MIN_BLOCKS_ODD
-#define LBM_VEC_MIN_BLOCKS_ODD 5
+#define LBM_VEC_MIN_BLOCKS_ODD 4     // 128 registers: the odd phase keeps nine float4 loads in flight next to the 36 population registers
 #endif
+// CM<2,OptimalAdapter> carries the adapter quantities and partial sums on top
+#ifndef LBM_VEC_MIN_BLOCKS_EVEN_OPT
+#define LBM_VEC_MIN_BLOCKS_EVEN_OPT 5
+#endif
+#ifndef LBM_VEC_MIN_BLOCKS_ODD_OPT
+#define LBM_VEC_MIN_BLOCKS_ODD_OPT 4
+#endif
+constexpr int vec_min_blocks(int coll, bool odd) {
+    return coll == 3 ? (odd ? LBM_VEC_MIN_BLOCKS_ODD_OPT : LBM_VEC_MIN_BLOCKS_EVEN_OPT) : (odd ? LBM_VEC_MIN_BLOCKS_ODD : LBM_VEC_MIN_BLOCKS_EVEN);
+}
 
-__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
-__device__ __forceinline__ void st4(float* p, float a, float b, float c, float d) { *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d); }
+// cache hints of the population accesses (every population is read once and written once per step):
+// LBM_LD_HINT 0 plain, 1 ld.global.cs (streaming), 2 ld.global.lu (last use); LBM_ST_HINT 0 plain, 1 st.global.cs, 2 st.global.wt
+#ifndef LBM_LD_HINT
+#define LBM_LD_HINT 0
+#endif
+#ifndef LBM_ST_HINT
+#define LBM_ST_HINT 0
+#endif
+__device__ __forceinline__ float4 ld4(const float* p) {
+#if LBM_LD_HINT == 1
+    return __ldcs(reinterpret_cast<const float4*>(p));
+#elif LBM_LD_HINT == 2
+    return __ldlu(reinterpret_cast<const float4*>(p));
+#else
+    return *reinterpret_cast<const float4*>(p);
+#endif
+}
+__device__ __forceinline__ void st4(float* p, float a, float b, float c, float d) {
+#if LBM_ST_HINT == 1
+    __stcs(reinterpret_cast<float4*>(p), make_float4(a, b, c, d));
+#elif LBM_ST_HINT == 2
+    __stwt(reinterpret_cast<float4*>(p), make_float4(a, b, c, d));
+#else
+    *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
+#endif
+}
 
 // f[0..3] of cells x0..x0+3 go to x0+1 .. x0+4
 __device__ __forceinline__ void store_to_right(float* r, int x0, int xr, bool hasL, bool hasR, bool act, const float f[4]) {
@@ -128,8 +177,93 @@ __device__ __forceinline__ void store_to_left(float* r, int x0, int xl, bool has
     if (!hasL) r[xl] = f[0];
 }
 
+// Where a thread of the vectorised kernels works: cells x0 .. x0+3 of row yl, and how it reaches rows y-1 / y+1.
+struct VecCtx {
+    int yl, x0, xl, xr, gen;
+    bool act, hasL, hasR;
+    long long r0;
+    float *bm, *bp;             // rows y-1 / y+1 of plane k start at bm + k*sm / bp + k*sp: this slab, its ghost rows, or (peer-mapped) the neighbour slab
+    long long sm, sp;
+};
+
+// returns false for warps that have nothing to do (beyond the row end, or a segment the general kernel owns)
+template <bool ODD>
+__device__ __forceinline__ bool vec_setup(const Params& p, VecCtx& c) {
+    const int nv = p.nx >> 2;
+    const int xv_raw = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    c.yl = blockIdx.y;
+    c.act = xv_raw < nv;
+    const int xv = c.act ? xv_raw : nv - 1;           // idle lanes of the last warp shadow a valid cell (loads only)
+    bool warp_on = (xv_raw & ~31) < nv;               // warp-uniform: one warp = one 128-cell segment
+    if (warp_on && p.segmask) warp_on = p.segmask[(long long)c.yl * p.nsx + (xv_raw >> 5)] == 0;
+    if (!warp_on) return false;
+    c.x0 = xv << 2;
+    c.r0 = rowoff(p, c.yl);
+    c.gen = p.t & 1;
+    // neighbours inside the warp exchange the boundary element; a row starts at lane 0 (blockDim.x % 32 == 0)
+    c.hasL = lane > 0; c.hasR = lane < 31 && xv_raw < nv - 1;
+    c.xl = c.x0 - 1; c.xr = c.x0 + 4;
+    if (c.xl < 0) c.xl += p.nx;
+    if (c.xr >= p.nx) c.xr -= p.nx;
+    int ym = c.yl - 1, yp = c.yl + 1;
+    if (p.wrap_y) { if (ym < 0) ym += p.nyl; if (yp >= p.nyl) yp -= p.nyl; }
+    c.bm = p.A[0] + rowoff(p, ym); c.sm = p.plane;
+    c.bp = p.A[0] + rowoff(p, yp); c.sp = p.plane;
+    if (ODD) {
+        if (ym < 0 && p.peer[0]) { c.bm = p.peer[0] + p.peer_off[0]; c.sm = p.peer_plane[0]; }
+        if (yp >= p.nyl && p.peer[1]) { c.bp = p.peer[1] + p.peer_off[1]; c.sp = p.peer_plane[1]; }
+    }
+    return true;
+}
+
+// post-stream populations of the thread's four cells: g[h][q] holds cells x0+2h, x0+2h+1 side by side (packed fp32 lanes)
+template <bool ODD>
+__device__ __forceinline__ void vec_load(const Params& p, const VecCtx& c, V2 g[2][Q]) {
+    const int x0 = c.x0;
+    {
+        float4 v = ld4(p.A0[c.gen] + c.r0 + x0);
+        g[0][0].a = make_float2(v.x, v.y); g[1][0].a = make_float2(v.z, v.w);
+    }
+    if (!ODD) {
+#pragma unroll
+        for (int q = 1; q < Q; q++) {
+            float4 v = ld4(p.A[q] + c.r0 + x0);
+            g[0][q].a = make_float2(v.x, v.y); g[1][q].a = make_float2(v.z, v.w);
+        }
+    } else {
+        // g_q(x) = A[opp q][x - c_q]: source row y - c_y, source column x - c_x.  All vector loads first, then the
+        // (predicated) scalar loads of the first / last lane, then the shuffles -- nothing between the loads that
+        // would make them wait for one another.
+        float4 v[Q]; float e[Q];
+#pragma unroll
+        for (int q = 1; q < Q; q++) {
+            const float* r = cy(q) > 0 ? c.bm + opp(q) * c.sm : (cy(q) < 0 ? c.bp + opp(q) * c.sp : p.A[opp(q)] + c.r0);
+            v[q] = ld4(r + x0);
+            e[q] = 0.f;
+            if (cx(q) > 0) { if (!c.hasL) e[q] = r[c.xl]; }
+            else if (cx(q) < 0) { if (!c.hasR) e[q] = r[c.xr]; }
+        }
+#pragma unroll
+        for (int q = 1; q < Q; q++) {
+            if (cx(q) > 0) {
+                float l = __shfl_up_sync(FULL, v[q].w, 1);
+                if (!c.hasL) l = e[q];
+                g[0][q].a = make_float2(l, v[q].x); g[1][q].a = make_float2(v[q].y, v[q].z);
+            } else if (cx(q) < 0) {
+                float rr = __shfl_down_sync(FULL, v[q].x, 1);
+                if (!c.hasR) rr = e[q];
+                g[0][q].a = make_float2(v[q].y, v[q].z); g[1][q].a = make_float2(v[q].w, rr);
+            } else { g[0][q].a = make_float2(v[q].x, v[q].y); g[1][q].a = make_float2(v[q].z, v[q].w); }
+        }
+    }
+}
+
+// NOTE: setup and loads are written out inside this kernel on purpose.  Routing them through vec_setup / vec_load (as the
+// moments pre-pass does) is semantically identical but changed nvcc's schedule enough to cost 12 % on the odd phase
+// (5.80 vs 6.58 TB/s at 16384^2, profiles/r01_kbench_packed.txt), with the same register count.
 template <int COLL, bool ODD>
-__global__ void __launch_bounds__(BX, ODD ? LBM_VEC_MIN_BLOCKS_ODD : LBM_VEC_MIN_BLOCKS_EVEN) step_vec_kernel(const Params p) {
+__global__ void __launch_bounds__(BX, vec_min_blocks(COLL, ODD)) step_vec_kernel(const Params p) {
     const int nv = p.nx >> 2;
     const int xv_raw = blockIdx.x * blockDim.x + threadIdx.x;
     const int yl = blockIdx.y;
@@ -143,7 +277,7 @@ __global__ void __launch_bounds__(BX, ODD ? LBM_VEC_MIN_BLOCKS_ODD : LBM_VEC_MIN
         const int x0 = xv << 2;
         const long long r0 = rowoff(p, yl);
         const int gen = p.t & 1;
-        float g[4][Q];
+        V2 g[2][Q];                                   // g[h][q]: cells x0+2h, x0+2h+1 side by side (packed fp32 lanes)
         // neighbours inside the warp exchange the boundary element; a row starts at lane 0 (blockDim.x % 32 == 0)
         const bool hasL = lane > 0, hasR = lane < 31 && xv_raw < nv - 1;
         int xl = x0 - 1, xr = x0 + 4;
@@ -160,13 +294,13 @@ __global__ void __launch_bounds__(BX, ODD ? LBM_VEC_MIN_BLOCKS_ODD : LBM_VEC_MIN
         }
         {
             float4 v = ld4(p.A0[gen] + r0 + x0);
-            g[0][0] = v.x; g[1][0] = v.y; g[2][0] = v.z; g[3][0] = v.w;
+            g[0][0].a = make_float2(v.x, v.y); g[1][0].a = make_float2(v.z, v.w);
         }
         if (!ODD) {
 #pragma unroll
             for (int q = 1; q < Q; q++) {
                 float4 v = ld4(p.A[q] + r0 + x0);
-                g[0][q] = v.x; g[1][q] = v.y; g[2][q] = v.z; g[3][q] = v.w;
+                g[0][q].a = make_float2(v.x, v.y); g[1][q].a = make_float2(v.z, v.w);
             }
         } else {
             // g_q(x) = A[opp q][x - c_q]: source row y - c_y, source column x - c_x.  All vector loads first, then the
@@ -186,52 +320,57 @@ __global__ void __launch_bounds__(BX, ODD ? LBM_VEC_MIN_BLOCKS_ODD : LBM_VEC_MIN
                 if (cx(q) > 0) {
                     float l = __shfl_up_sync(FULL, v[q].w, 1);
                     if (!hasL) l = e[q];
-                    g[0][q] = l; g[1][q] = v[q].x; g[2][q] = v[q].y; g[3][q] = v[q].z;
+                    g[0][q].a = make_float2(l, v[q].x); g[1][q].a = make_float2(v[q].y, v[q].z);
                 } else if (cx(q) < 0) {
                     float rr = __shfl_down_sync(FULL, v[q].x, 1);
                     if (!hasR) rr = e[q];
-                    g[0][q] = v[q].y; g[1][q] = v[q].z; g[2][q] = v[q].w; g[3][q] = rr;
-                } else { g[0][q] = v[q].x; g[1][q] = v[q].y; g[2][q] = v[q].z; g[3][q] = v[q].w; }
+                    g[0][q].a = make_float2(v[q].y, v[q].z); g[1][q].a = make_float2(v[q].w, rr);
+                } else { g[0][q].a = make_float2(v[q].x, v[q].y); g[1][q].a = make_float2(v[q].z, v[q].w); }
             }
         }
-        float rho4[4], ux4[4], uy4[4];
+        float2 rho4[2], ux4[2], uy4[2];
         AdapterAvg av{};
         if (COLL == C_CMOPT) av = load_adapter_avg(p.avg);
+        const Relax rx = relax_of(p);
+        const bool forced = p.fx != 0.0f || p.fy != 0.0f;      // uniform body force only: everything else takes the general path
+        const V2 Fx = splat<V2>(p.fx), Fy = splat<V2>(p.fy);
+        V2 acc0 = splat<V2>(0.f), acc1 = acc0, acc2 = acc0;
 #pragma unroll
-        for (int c = 0; c < 4; c++) {
-            Moments m = moments(g[c]);
-            const float Fx = p.fx, Fy = p.fy;
-            const float h = 0.5f * m.inv_rho;
-            const float ux = m.ux + Fx * h, uy = m.uy + Fy * h;
-            rho4[c] = m.rho; ux4[c] = ux; uy4[c] = uy;
-            if (COLL == C_BGK) collide_bgk(p, g[c], m.rho, ux, uy, Fx, Fy);
-            else if (COLL == C_MRT) collide_mrt(p, g[c], m.rho, ux, uy, Fx, Fy);
-            else if (COLL == C_CM) collide_cm<false>(p, g[c], ux, uy, Fx, Fy);
+        for (int hf = 0; hf < 2; hf++) {
+            const Mom<V2> m = moments_v(g[hf]);
+            // correct_macroscopics_kernel<2> (macroscopics.cu:99-110): u += F / (2 rho)
+            V2 ux = m.ux, uy = m.uy;
+            if (forced) { const V2 hr = m.inv_rho * 0.5f; ux = fma(Fx, hr, ux); uy = fma(Fy, hr, uy); }
+            rho4[hf] = m.rho.a; ux4[hf] = ux.a; uy4[hf] = uy.a;
+            if (COLL == C_BGK) collide_bgk_v(rx, g[hf], m.rho, ux, uy, forced, Fx, Fy);
+            else if (COLL == C_MRT) collide_mrt_v(rx, g[hf], m.rho, ux, uy, forced, Fx, Fy);
+            else if (COLL == C_CM) collide_cm_v<false>(rx, g[hf], ux, uy, forced, Fx, Fy, splat<V2>(1.0f));
             else {
-                const float jmag = sqrtf(ux * ux + uy * uy) * m.rho, pimag = pi_norm(m);
-                if (act) { s0 += m.rho; s1 += jmag; s2 += pimag; }
-                collide_cm<true>(p, g[c], ux, uy, Fx, Fy, jmag, pimag, &av);
+                const V2 jm = jmag_v(ux, uy, m.rho), pm = pi_norm_v(m);
+                acc0 = acc0 + m.rho; acc1 = acc1 + jm; acc2 = acc2 + pm;
+                collide_cm_v<true>(rx, g[hf], ux, uy, forced, Fx, Fy, optimal_rate_v(m.rho, jm, pm, av));
             }
         }
+        if (COLL == C_CMOPT && act) { s0 = hsum(acc0); s1 = hsum(acc1); s2 = hsum(acc2); }
         if (p.rho_out && act) {
             const long long ln = (long long)yl * p.nx + x0;
-            st4(p.rho_out + ln, rho4[0], rho4[1], rho4[2], rho4[3]);
+            st4(p.rho_out + ln, rho4[0].x, rho4[0].y, rho4[1].x, rho4[1].y);
             float* uo = reinterpret_cast<float*>(p.u_out + ln);
-            st4(uo, ux4[0], uy4[0], ux4[1], uy4[1]);
-            st4(uo + 4, ux4[2], uy4[2], ux4[3], uy4[3]);
+            st4(uo, ux4[0].x, uy4[0].x, ux4[0].y, uy4[0].y);
+            st4(uo + 4, ux4[1].x, uy4[1].x, ux4[1].y, uy4[1].y);
         }
-        if (act) st4(p.A0[gen] + r0 + x0, g[0][0], g[1][0], g[2][0], g[3][0]);
+        if (act) st4(p.A0[gen] + r0 + x0, g[0][0].a.x, g[0][0].a.y, g[1][0].a.x, g[1][0].a.y);
         if (!ODD) {
             if (act) {
 #pragma unroll
-                for (int q = 1; q < Q; q++) st4(p.A[opp(q)] + r0 + x0, g[0][q], g[1][q], g[2][q], g[3][q]);
+                for (int q = 1; q < Q; q++) st4(p.A[opp(q)] + r0 + x0, g[0][q].a.x, g[0][q].a.y, g[1][q].a.x, g[1][q].a.y);
             }
         } else {
 #pragma unroll
             for (int q = 1; q < Q; q++) {
                 // f*_q(x) -> A[q][x + c_q]: destination row y + c_y, destination column x + c_x
                 float* r = cy(q) > 0 ? bp + q * sp : (cy(q) < 0 ? bm + q * sm : p.A[q] + r0);
-                const float f[4] = {g[0][q], g[1][q], g[2][q], g[3][q]};
+                const float f[4] = {g[0][q].a.x, g[0][q].a.y, g[1][q].a.x, g[1][q].a.y};
                 if (cx(q) > 0) store_to_right(r, x0, xr, hasL, hasR, act, f);
                 else if (cx(q) < 0) store_to_left(r, x0, xl, hasL, hasR, act, f);
                 else if (act) st4(r + x0, f[0], f[1], f[2], f[3]);
@@ -241,16 +380,47 @@ __global__ void __launch_bounds__(BX, ODD ? LBM_VEC_MIN_BLOCKS_ODD : LBM_VEC_MIN
     if (COLL == C_CMOPT && p.partials) block_partials(s0, s1, s2, p.partials + 3 * ((long long)blockIdx.y * gridDim.x + blockIdx.x));
 }
 
-// moments pre-pass for LBM_ADAPTER_EXACT: the grid sums of the CURRENT post-stream state, before any cell collides
+// moments pre-pass for LBM_ADAPTER_EXACT: the grid sums of the CURRENT post-stream state, before any cell collides.
+// Same two launch shapes as the step: this scalar kernel over the whole slab or over the listed general segments ...
 template <bool ODD>
 __global__ void __launch_bounds__(BX) moments_kernel(const Params p) {
-    const int x = blockIdx.x * BX + threadIdx.x;
-    const int yl = blockIdx.y;
+    int x, yl;
+    if (p.gen_list) {
+        const int seg = p.gen_list[blockIdx.x];
+        yl = seg / p.nsx;
+        x = (seg - yl * p.nsx) * SEG + threadIdx.x;
+    } else {
+        x = blockIdx.x * BX + threadIdx.x;
+        yl = blockIdx.y;
+    }
     float s0 = 0.f, s1 = 0.f, s2 = 0.f;
     if (x < p.nx) {
         NodeState s;
         node_pre_collision<ODD, true>(p, x, yl, s);
-        s0 = s.m.rho; s1 = sqrtf(s.ux * s.ux + s.uy * s.uy) * s.m.rho; s2 = pi_norm(s.m);
+        const V1 rho{s.m.rho};
+        s0 = s.m.rho; s1 = jmag_v(V1{s.ux}, V1{s.uy}, rho).a;
+        s2 = pi_norm_v(Mom<V1>{rho, V1{s.m.inv_rho}, V1{s.m.ux}, V1{s.m.uy}, V1{s.m.pxx}, V1{s.m.pxy}, V1{s.m.pyy}}).a;
+    }
+    block_partials(s0, s1, s2, p.partials + 3 * ((long long)blockIdx.y * gridDim.x + blockIdx.x));
+}
+// ... and the vectorised one over everything else (36 B/cell read, nothing written)
+template <bool ODD>
+__global__ void __launch_bounds__(BX, 6) moments_vec_kernel(const Params p) {
+    VecCtx c;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    if (vec_setup<ODD>(p, c)) {
+        V2 g[2][Q];
+        vec_load<ODD>(p, c, g);
+        const bool forced = p.fx != 0.0f || p.fy != 0.0f;
+        V2 acc0 = splat<V2>(0.f), acc1 = acc0, acc2 = acc0;
+#pragma unroll
+        for (int hf = 0; hf < 2; hf++) {
+            const Mom<V2> m = moments_v(g[hf]);
+            V2 ux = m.ux, uy = m.uy;
+            if (forced) { const V2 hr = m.inv_rho * 0.5f; ux = fma(splat<V2>(p.fx), hr, ux); uy = fma(splat<V2>(p.fy), hr, uy); }
+            acc0 = acc0 + m.rho; acc1 = acc1 + jmag_v(ux, uy, m.rho); acc2 = acc2 + pi_norm_v(m);
+        }
+        if (c.act) { s0 = hsum(acc0); s1 = hsum(acc1); s2 = hsum(acc2); }
     }
     block_partials(s0, s1, s2, p.partials + 3 * ((long long)blockIdx.y * gridDim.x + blockIdx.x));
 }
