@@ -210,8 +210,8 @@ def main():
     achieved = BYTES_PER_UPDATE * nloc / (kern_ms * 1e-3) / 1e9
     peak, peak_src = measured_peak()
     # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of this very command
-    # (profiles/r01_ncu_bench_kernel.md: 77.355 GB odd phase, 77.259 GB even phase); other sizes were not captured
-    traffic = 77.307e9 * (nloc / float(NX * NY)) if (nx == NX and args.collision == "BGK") else None
+    # (profiles/r01_ncu_bench_kernel.md, second capture: 77.261 GB odd phase, 77.259 GB even phase); other sizes were not captured
+    traffic = 77.260e9 * (nloc / float(NX * NY)) if (nx == NX and args.collision == "BGK") else None
 
     # ---------------- end to end through the public API with host buffers ----------------
     e2e = None
