@@ -64,6 +64,7 @@ struct lbm_handle {
     // macroscopics
     float* rho_out = nullptr; float2* u_out = nullptr; int macros_ts = -1;
     double* mass_acc = nullptr;
+    double* val_stage = nullptr; long long val_stage_n = 0;      // validation reductions (lbm_*_error_sums, lbm_row_mean_velocity)
     int timestep = 0;
     long long launches = 0;
     long long bytes = 0;
@@ -143,7 +144,7 @@ extern "C" int lbm_destroy(lbm_handle* h) {
         if (h->peer[sd].ipc_base && !(sd == 1 && h->peer[0].ipc_base == h->peer[1].ipc_base)) cudaIpcCloseMemHandle(h->peer[sd].ipc_base);
     void* ptrs[] = {h->sync_timeout, h->pop, h->flags, h->force_plane, h->ring, h->nbr_nodes, h->nbr_src, h->nbr_g, h->d_pts, h->ibm_nodes,
                     h->sten_idx, h->sten_w, h->csr_row, h->csr_k, h->csr_w, h->ibm_rho, h->ibm_uprev, h->ibm_lagF, h->ibm_force,
-                    h->partials, h->stage, h->sums, h->avg, h->rho_out, h->u_out, h->mass_acc, h->segmask, h->gen_list};
+                    h->partials, h->stage, h->sums, h->avg, h->rho_out, h->u_out, h->mass_acc, h->segmask, h->gen_list, h->val_stage};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
@@ -756,6 +757,167 @@ extern "C" int lbm_total_mass(lbm_handle* h, double* out) {
     CU(cudaStreamSynchronize(h->stream));
     return LBM_OK;
 }
+
+// ------------------------------------------------------------------ validation reductions on the device
+static int need_current_macros(lbm_handle* h) {
+    if (h->macros_ts != h->timestep || !h->rho_out)
+        return fail(LBM_ERR_STATE, "macroscopics of the current timestep were not produced: run the last step with lbm_step_with_macroscopics");
+    return LBM_OK;
+}
+static int ensure_val_stage(lbm_handle* h, long long n) {
+    if (n <= h->val_stage_n) return LBM_OK;
+    if (h->val_stage) { CU(cudaStreamSynchronize(h->stream)); cudaFree(h->val_stage); h->bytes -= 8 * h->val_stage_n; h->val_stage = nullptr; }
+    CU(dmalloc(h, &h->val_stage, (size_t)n));
+    h->val_stage_n = n;
+    return LBM_OK;
+}
+
+static int error_sums(lbm_handle* h, const float2* d_ref, bool tg, float nu, float u0, float t, double out[2]) {
+    if (!h || !out) return fail(LBM_ERR_INVALID, "NULL argument");
+    int rc = need_current_macros(h); if (rc) return rc;
+    CU(cudaSetDevice(h->cfg.device));
+    rc = ensure_val_stage(h, 2 * (RED_BLOCKS + 1)); if (rc) return rc;
+    const int nb = (int)std::min<long long>(RED_BLOCKS, (h->nloc + 255) / 256);
+    if (tg) error_sums_kernel<true><<<nb, 256, 0, h->stream>>>(h->u_out, nullptr, h->cfg.nx, h->cfg.ny, h->y0, h->nloc, nu, u0, t, h->val_stage);
+    else error_sums_kernel<false><<<nb, 256, 0, h->stream>>>(h->u_out, d_ref, h->cfg.nx, h->cfg.ny, h->y0, h->nloc, 0.f, 0.f, 0.f, h->val_stage);
+    error_sums_final_kernel<<<1, 256, 0, h->stream>>>(h->val_stage, nb, h->val_stage + 2 * RED_BLOCKS);
+    h->launches += 2;
+    CU(cudaMemcpyAsync(out, h->val_stage + 2 * RED_BLOCKS, 16, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    return LBM_OK;
+}
+
+extern "C" int lbm_velocity_error_sums(lbm_handle* h, const float* d_u_ref, double out[2]) {
+    if (!d_u_ref) return fail(LBM_ERR_INVALID, "NULL argument");
+    return error_sums(h, (const float2*)d_u_ref, false, 0.f, 0.f, 0.f, out);
+}
+extern "C" int lbm_taylor_green_error_sums(lbm_handle* h, float nu, float u0, float t, double out[2]) {
+    return error_sums(h, nullptr, true, nu, u0, t, out);
+}
+
+extern "C" int lbm_row_mean_velocity(lbm_handle* h, double* mean_ux, double* mean_uy) {
+    if (!h || !mean_ux || !mean_uy) return fail(LBM_ERR_INVALID, "NULL argument");
+    int rc = need_current_macros(h); if (rc) return rc;
+    CU(cudaSetDevice(h->cfg.device));
+    rc = ensure_val_stage(h, std::max<long long>(2 * (RED_BLOCKS + 1), 2ll * h->nyl)); if (rc) return rc;
+    row_mean_kernel<<<h->nyl, 256, 0, h->stream>>>(h->u_out, h->cfg.nx, h->val_stage, h->val_stage + h->nyl);
+    h->launches++;
+    CU(cudaMemcpyAsync(mean_ux, h->val_stage, (size_t)h->nyl * 8, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(mean_uy, h->val_stage + h->nyl, (size_t)h->nyl * 8, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    return LBM_OK;
+}
+
+// ------------------------------------------------------------------ checkpoint / restart
+// File = CkptHeader + the population planes exactly as they sit in HBM (AA phase included, ghost rows included) + the edge
+// ring.  Everything else a step reads is either configuration (re-created by the caller: flags, bodies, forces) or rebuilt
+// from the populations at the start of the step (neighbour-BC gather, IBM, adapter sums in LBM_ADAPTER_EXACT).
+struct CkptHeader {
+    char magic[8];
+    uint32_t version, header_bytes;
+    int32_t nx, ny, rank, world, y0, nyl, nplanes, collision, quirks, periodic_x, periodic_y, adapter_mode;
+    int32_t timestep, avg_for_ts, perim, pad;
+    float avg[3]; float pad2;
+    double sums[3];
+    uint64_t pop_floats, ring_floats;
+};
+static const char kCkptMagic[8] = {'L', 'B', 'M', 'B', '2', '0', '0', 1};
+constexpr size_t CKPT_CHUNK = (size_t)32 << 20;         // bytes per pinned staging buffer (two of them)
+
+static CkptHeader ckpt_header(const lbm_handle* h) {
+    CkptHeader k{};
+    memcpy(k.magic, kCkptMagic, 8);
+    k.version = 1; k.header_bytes = (uint32_t)sizeof(CkptHeader);
+    k.nx = h->cfg.nx; k.ny = h->cfg.ny; k.rank = h->cfg.rank; k.world = h->cfg.world; k.y0 = h->y0; k.nyl = h->nyl;
+    k.nplanes = h->nplanes; k.collision = h->cfg.collision; k.quirks = h->cfg.quirks;
+    k.periodic_x = h->cfg.periodic_x; k.periodic_y = h->cfg.periodic_y; k.adapter_mode = h->cfg.adapter_mode;
+    k.timestep = h->timestep; k.avg_for_ts = h->avg_for_ts; k.perim = h->perim;
+    k.pop_floats = (uint64_t)h->plane * h->nplanes; k.ring_floats = (uint64_t)2 * h->perim * Q;
+    return k;
+}
+
+extern "C" int lbm_checkpoint_bytes(lbm_handle* h, int64_t* out) {
+    if (!h || !out) return fail(LBM_ERR_INVALID, "NULL argument");
+    CkptHeader k = ckpt_header(h);
+    *out = (int64_t)(sizeof(CkptHeader) + 4 * (k.pop_floats + k.ring_floats));
+    return LBM_OK;
+}
+
+// device <-> file through two pinned staging buffers: the copy of chunk i+1 runs while chunk i is written / read
+static int stream_region(lbm_handle* h, FILE* fp, char* dev, size_t bytes, bool save, char* stage[2], cudaEvent_t ev[2]) {
+    const size_t n = (bytes + CKPT_CHUNK - 1) / CKPT_CHUNK;
+    auto len = [&](size_t i) { return std::min(CKPT_CHUNK, bytes - i * CKPT_CHUNK); };
+    if (save) {
+        for (size_t i = 0; i <= n; i++) {
+            if (i < n) {
+                CU(cudaMemcpyAsync(stage[i & 1], dev + i * CKPT_CHUNK, len(i), cudaMemcpyDeviceToHost, h->stream));
+                CU(cudaEventRecord(ev[i & 1], h->stream));
+            }
+            if (i > 0) {
+                CU(cudaEventSynchronize(ev[(i - 1) & 1]));
+                if (fwrite(stage[(i - 1) & 1], 1, len(i - 1), fp) != len(i - 1)) return fail(LBM_ERR_STATE, "checkpoint: short write");
+            }
+        }
+    } else {
+        for (size_t i = 0; i < n; i++) {
+            if (i >= 2) CU(cudaEventSynchronize(ev[i & 1]));       // the copy that last used this buffer
+            if (fread(stage[i & 1], 1, len(i), fp) != len(i)) return fail(LBM_ERR_STATE, "checkpoint: file is truncated");
+            CU(cudaMemcpyAsync(dev + i * CKPT_CHUNK, stage[i & 1], len(i), cudaMemcpyHostToDevice, h->stream));
+            CU(cudaEventRecord(ev[i & 1], h->stream));
+        }
+        CU(cudaStreamSynchronize(h->stream));
+    }
+    return LBM_OK;
+}
+
+static int checkpoint_io(lbm_handle* h, const char* path, bool save) {
+    if (!h || !path) return fail(LBM_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaStreamSynchronize(h->stream));
+    FILE* fp = fopen(path, save ? "wb" : "rb");
+    if (!fp) return fail(LBM_ERR_INVALID, std::string("checkpoint: cannot open ") + path);
+    CkptHeader k = ckpt_header(h);
+    int rc = LBM_OK;
+    if (save) {
+        if (cudaMemcpy(k.avg, h->avg, 12, cudaMemcpyDeviceToHost) != cudaSuccess || cudaMemcpy(k.sums, h->sums, 24, cudaMemcpyDeviceToHost) != cudaSuccess)
+            rc = fail(LBM_ERR_CUDA, "checkpoint: reading the adapter means failed");
+        else if (fwrite(&k, sizeof(k), 1, fp) != 1) rc = fail(LBM_ERR_STATE, "checkpoint: short write");
+    } else {
+        CkptHeader f{};
+        if (fread(&f, sizeof(f), 1, fp) != 1 || memcmp(f.magic, kCkptMagic, 8) != 0 || f.version != 1 || f.header_bytes != sizeof(CkptHeader))
+            rc = fail(LBM_ERR_INVALID, "checkpoint: not a checkpoint file of this engine version");
+        else if (f.nx != k.nx || f.ny != k.ny || f.rank != k.rank || f.world != k.world || f.y0 != k.y0 || f.nyl != k.nyl || f.nplanes != k.nplanes ||
+                 f.periodic_x != k.periodic_x || f.periodic_y != k.periodic_y || f.pop_floats != k.pop_floats || f.ring_floats != k.ring_floats)
+            rc = fail(LBM_ERR_INVALID, "checkpoint: written for a different grid / slab decomposition / quirk set (nx, ny, rank, world, periodicity and LBM_QK_D1_STALE_F0 must match)");
+        else k = f;
+    }
+    char* stage[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    if (rc == LBM_OK) {
+        for (int i = 0; i < 2 && rc == LBM_OK; i++)
+            if (cudaHostAlloc((void**)&stage[i], CKPT_CHUNK, cudaHostAllocDefault) != cudaSuccess || cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) != cudaSuccess)
+                rc = fail(LBM_ERR_CUDA, "checkpoint: pinned staging allocation failed");
+    }
+    if (rc == LBM_OK) rc = stream_region(h, fp, (char*)h->pop, (size_t)k.pop_floats * 4, save, stage, ev);
+    if (rc == LBM_OK) rc = stream_region(h, fp, (char*)h->ring, (size_t)k.ring_floats * 4, save, stage, ev);
+    for (int i = 0; i < 2; i++) { if (stage[i]) cudaFreeHost(stage[i]); if (ev[i]) cudaEventDestroy(ev[i]); }
+    if (fclose(fp) != 0 && rc == LBM_OK && save) rc = fail(LBM_ERR_STATE, "checkpoint: close failed");
+    if (rc != LBM_OK || save) return rc;
+    // restart: the scalar state of the handle
+    h->timestep = k.timestep; h->avg_for_ts = k.avg_for_ts; h->pre_for_ts = -1; h->macros_ts = -1;
+    CU(cudaMemcpy(h->avg, k.avg, 12, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(h->sums, k.sums, 24, cudaMemcpyHostToDevice));
+    // peer-mapped neighbours restart from the same step: all slabs must have loaded (host barrier) before any of them steps
+    unsigned long long fl[2] = {(unsigned long long)k.timestep, (unsigned long long)k.timestep};
+    CU(cudaMemcpy(h->sync_flags, fl, 16, cudaMemcpyHostToDevice));
+    CU(cudaMemset(h->sync_timeout, 0, sizeof(int)));
+    return LBM_OK;
+}
+
+extern "C" int lbm_checkpoint_write(lbm_handle* h, const char* path) { return checkpoint_io(h, path, true); }
+extern "C" int lbm_checkpoint_read(lbm_handle* h, const char* path) { return checkpoint_io(h, path, false); }
 
 extern "C" int lbm_moment_avg(lbm_handle* h, float out[3]) {
     if (!h || !out) return fail(LBM_ERR_INVALID, "NULL argument");

@@ -716,4 +716,56 @@ __global__ void __launch_bounds__(BX) mass_kernel(const Params p, double* out) {
     if (threadIdx.x == 0) atomicAdd(out, sm[0]);
 }
 
+// ------------------------------------------------------------------ validation reductions (deterministic, fp64)
+// TaylorGreenValidation::operator() — reference src/scenarios/taylorGreen/taylorGreenFunctors.cuh:66-81 (u0 = its u_max/SCALE)
+__device__ __forceinline__ float2 taylor_green_analytic(int xi, int yi, int nx, int ny, float nu, float u0, float t) {
+    const float x = xi + 0.5f, y = yi + 0.5f;
+    const float kx = 2.0f * (float)3.14159265358979323846 / nx, ky = 2.0f * (float)3.14159265358979323846 / ny;
+    const float td = 1.0f / (nu * (kx * kx + ky * ky));
+    const float decay = expf(-t / td);
+    return make_float2(-u0 * sqrtf(ky / kx) * cosf(kx * x) * sinf(ky * y) * decay, u0 * sqrtf(kx / ky) * sinf(kx * x) * cosf(ky * y) * decay);
+}
+
+__device__ __forceinline__ void block_sum2(double a, double b, double* out) {
+    __shared__ double sm[2][256];
+    sm[0][threadIdx.x] = a; sm[1][threadIdx.x] = b;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) { sm[0][threadIdx.x] += sm[0][threadIdx.x + s]; sm[1][threadIdx.x] += sm[1][threadIdx.x + s]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { out[0] = sm[0][0]; out[1] = sm[1][0]; }
+}
+
+// the two sums of Scenario::compute_error (taylorGreenScenario.cuh:66-87): sum |u - u_ref|^2 and sum |u_ref|^2 over this slab;
+// u_ref from a device field (AoS, slab rows) or, TG = true, the analytic Taylor-Green field evaluated in place
+template <bool TG>
+__global__ void __launch_bounds__(256) error_sums_kernel(const float2* u, const float2* ref, int nx, int ny, int y0, long long n, float nu, float u0, float t, double* stage) {
+    double e = 0.0, r = 0.0;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+        float2 a;
+        if (TG) { const int yl = (int)(i / nx); a = taylor_green_analytic((int)(i - (long long)yl * nx), y0 + yl, nx, ny, nu, u0, t); }
+        else a = ref[i];
+        const float2 s = u[i];
+        const float dx = s.x - a.x, dy = s.y - a.y;
+        e += (double)(dx * dx + dy * dy);
+        r += (double)(a.x * a.x + a.y * a.y);
+    }
+    block_sum2(e, r, stage + 2 * blockIdx.x);
+}
+__global__ void __launch_bounds__(256) error_sums_final_kernel(const double* stage, int n, double* out) {
+    double e = 0.0, r = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) { e += stage[2 * i]; r += stage[2 * i + 1]; }
+    block_sum2(e, r, out);
+}
+// mean of u over x for every row of the slab (the inner loop of PoiseuilleScenario::compute_error, poiseuilleScenario.cuh:63-70)
+__global__ void __launch_bounds__(256) row_mean_kernel(const float2* u, int nx, double* mean_ux, double* mean_uy) {
+    const float2* row = u + (long long)blockIdx.x * nx;
+    double a = 0.0, b = 0.0;
+    for (int x = threadIdx.x; x < nx; x += 256) { const float2 v = row[x]; a += (double)v.x; b += (double)v.y; }
+    double o[2];
+    block_sum2(a, b, o);
+    if (threadIdx.x == 0) { mean_ux[blockIdx.x] = o[0] / nx; mean_uy[blockIdx.x] = o[1] / nx; }
+}
+
 }  // namespace lbm

@@ -155,6 +155,35 @@ class Engine:
     def adapter_prepass(self):
         check(lib().lbm_adapter_prepass(self._h))
 
+    # --- validation on the device (this slab's sums; add them over slabs) ---
+    def velocity_error_sums(self, d_u_ref_ptr):
+        o = (C.c_double * 2)()
+        check(lib().lbm_velocity_error_sums(self._h, C.c_void_p(d_u_ref_ptr), o))
+        return np.array([o[0], o[1]])
+
+    def taylor_green_error_sums(self, nu, u0, t):
+        o = (C.c_double * 2)()
+        check(lib().lbm_taylor_green_error_sums(self._h, float(np.float32(nu)), float(np.float32(u0)), float(np.float32(t)), o))
+        return np.array([o[0], o[1]])
+
+    def row_mean_velocity(self):
+        mx, my = np.empty(self.ny_local, np.float64), np.empty(self.ny_local, np.float64)
+        dp = C.POINTER(C.c_double)
+        check(lib().lbm_row_mean_velocity(self._h, mx.ctypes.data_as(dp), my.ctypes.data_as(dp)))
+        return mx, my
+
+    # --- checkpoint / restart ---
+    def checkpoint_bytes(self):
+        n = C.c_int64()
+        check(lib().lbm_checkpoint_bytes(self._h, C.byref(n)))
+        return n.value
+
+    def checkpoint_write(self, path):
+        check(lib().lbm_checkpoint_write(self._h, str(path).encode()))
+
+    def checkpoint_read(self, path):
+        check(lib().lbm_checkpoint_read(self._h, str(path).encode()))
+
     # --- peer-mapped neighbours ---
     def peer_export(self):
         buf = (C.c_ubyte * capi.PEER_DESC_BYTES)()

@@ -8,9 +8,11 @@
 // <dir with scenarios/...> is the reference's src/ (its scenario files compile unchanged) or examples/ (this repo's own).
 // Any other scenario:  -DSCENARIO_HEADER='"my/scenario.cuh"' -DSCENARIO_TYPE=MyScenario -DNX=.. -DNY=..
 //
-//   ./tg [--steps N] [--save-int K] [--vtk] [--dump] [--fast]
+//   ./tg [--steps N] [--save-int K] [--vtk] [--dump] [--fast] [--load-ckpt FILE] [--save-ckpt FILE]
 //     --save-int K  every K steps: update_macroscopics + compute_error (and --vtk: save_vtk, --dump: save_macroscopics)
 //     --fast        no per-step host calls between save points (LBM::run), the throughput mode
+//     --load-ckpt F continue from a checkpoint written by --save-ckpt (same binary); --steps counts the steps still to run
+//     --save-ckpt F write the population state after the last step
 #include <stdio.h>
 #include <cstring>
 #include <iostream>
@@ -41,12 +43,15 @@ using Scenario = FlowPastCylinderScenario;
 int main(int argc, char** argv) {
     int total_timesteps = 1000, save_int = 100;
     bool vtk = false, dump = false, fast = false;
+    const char *load_ckpt = nullptr, *save_ckpt = nullptr;
     for (int i = 1; i < argc; i++) {
         if (!strcmp(argv[i], "--steps") && i + 1 < argc) total_timesteps = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--save-int") && i + 1 < argc) save_int = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--vtk")) vtk = true;
         else if (!strcmp(argv[i], "--dump")) dump = true;
         else if (!strcmp(argv[i], "--fast")) fast = true;
+        else if (!strcmp(argv[i], "--load-ckpt") && i + 1 < argc) load_ckpt = argv[++i];
+        else if (!strcmp(argv[i], "--save-ckpt") && i + 1 < argc) save_ckpt = argv[++i];
         else { fprintf(stderr, "unknown argument %s\n", argv[i]); return 2; }
     }
     if (save_int <= 0) save_int = total_timesteps;
@@ -61,6 +66,11 @@ int main(int argc, char** argv) {
     LBM<dimensions> lbm;
     lbm.allocate<Scenario>();
     lbm.init<Scenario>();
+    if (load_ckpt) {
+        lbm.load_checkpoint<Scenario>(load_ckpt);
+        printf("restarted from %s at step %d\n", load_ckpt, lbm.timestep);
+    }
+    const int first_step = lbm.timestep;
 
     cudaEvent_t start, stop;
     cudaEventCreate(&start);
@@ -98,8 +108,16 @@ int main(int argc, char** argv) {
         if (dump) lbm.save_macroscopics(t);
         if constexpr (Scenario::has_analytical_solution) {
             last_error = lbm.compute_error<Scenario>();
-            printf("%s[%d]: error, %.4f%%\n", Scenario::name(), t, last_error);
+            printf("%s[%d]: error, %.4f%%\n", Scenario::name(), first_step + t, last_error);
+#ifndef LBM_B200_NO_DEVICE_ERROR      // needs a __host__ __device__ Validation::operator()(x, y, ux&, uy&), as the reference's are
+            if constexpr (lbm_b200_shim::is_field_validation<typename Scenario::ValidationType>::value)
+                printf("%s[%d]: L2 error taken on the device, %.4f%%\n", Scenario::name(), first_step + t, lbm.l2_error_device<Scenario>());
+#endif
         }
+    }
+    if (save_ckpt) {
+        lbm.save_checkpoint(save_ckpt);
+        printf("checkpoint of step %d written to %s\n", lbm.timestep, save_ckpt);
     }
     const double mass = lbm.total_mass();
     double sum_rho = 0.0, sum_u2 = 0.0;

@@ -52,8 +52,8 @@ struct B200AllFluid {
 struct B200TaylorGreenValidation {
     b200_tg::Field f;
     float t;
-    B200TaylorGreenValidation(float u_max, float nu, float t) : f{u_max / SCALE, nu}, t(t) {}
-    void operator()(int x, int y, float& ux, float& uy) const { float r; f.at(x, y, t, r, ux, uy); }
+    __host__ __device__ B200TaylorGreenValidation(float u_max, float nu, float t) : f{u_max / SCALE, nu}, t(t) {}
+    __host__ __device__ void operator()(int x, int y, float& ux, float& uy) const { float r; f.at(x, y, t, r, ux, uy); }
 };
 
 struct B200TaylorGreenScenario : public ScenarioTrait<B200TaylorGreenInit, B200AllFluid, B200TaylorGreenValidation, b200_op_by_id<B200_TG_OP>::type> {

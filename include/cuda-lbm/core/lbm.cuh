@@ -96,6 +96,21 @@ static __global__ void force_uniform_kernel(const float2* force, int n, int* dif
     if (a.x != b.x || a.y != b.y) *differs = 1;
 }
 
+// Validation functor over the whole grid: (x, y) -> analytic velocity (taylorGreenFunctors.cuh:66-81, poiseuilleFunctors.cuh:72-75)
+template <typename Validation>
+__global__ void validation_functor_kernel(Validation v, float2* u_ref, int nx, int ny) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)nx * ny) return;
+    float ux = 0.0f, uy = 0.0f;
+    v((int)(i % nx), (int)(i / nx), ux, uy);
+    u_ref[i] = make_float2(ux, uy);
+}
+
+// does the scenario's Validation functor map (x, y) to a velocity?  (void for scenarios without one; Ghia tables for the cavity)
+template <typename V, typename = void> struct is_field_validation : std::false_type {};
+template <typename V>
+struct is_field_validation<V, std::void_t<decltype(std::declval<const V&>()(0, 0, std::declval<float&>(), std::declval<float&>()))>> : std::true_type {};
+
 inline int env_int(const char* name, int fallback) {
     const char* v = std::getenv(name);
     return v ? std::atoi(v) : fallback;
@@ -345,6 +360,40 @@ public:
             printf("Scenario does not provide verification/validation.\n");
             return 0.0f;
         }
+    }
+
+    // extension: the relative L2 velocity error in percent against Scenario::validation() (the metric of
+    // taylorGreenScenario.cuh:59-88) with the functor evaluated and both sums taken on the device (fp64, fixed order):
+    // nothing but two doubles crosses PCIe, where compute_error<S>() moves 12 B/node to the host first
+    template <typename Scenario>
+    float l2_error_device() {
+        flush(true);
+        const long long n = (long long)NX * NY;
+        float2* d_ref = nullptr;
+        checkCudaErrors(cudaMalloc(&d_ref, (size_t)n * sizeof(float2)));
+        lbm_b200_shim::validation_functor_kernel<<<(unsigned)((n + 255) / 256), 256>>>(Scenario::validation(), d_ref, NX, NY);
+        checkCudaErrors(cudaGetLastError());
+        double sums[2] = {0.0, 0.0};
+        LBM_B200_CALL(lbm_velocity_error_sums(h, reinterpret_cast<const float*>(d_ref), sums));
+        checkCudaErrors(cudaFree(d_ref));
+        return (float)(std::sqrt(sums[0] / sums[1]) * 100.0);
+    }
+
+    // extension: checkpoint / restart of the population state (lbm_checkpoint_write / lbm_checkpoint_read).  load_checkpoint
+    // is called after allocate<S>() and init<S>() (which set flags, forces and bodies) and continues bit-identically.
+    void save_checkpoint(const std::string& path) {
+        flush(false);
+        LBM_B200_CALL(lbm_checkpoint_write(h, path.c_str()));
+    }
+    template <typename Scenario>
+    void load_checkpoint(const std::string& path) {
+        step_pending = false;
+        LBM_B200_CALL(lbm_checkpoint_read(h, path.c_str()));
+        lbm_info_t inf;
+        LBM_B200_CALL(lbm_info(h, &inf));
+        timestep = inf.timestep;
+        update_ts = -1;
+        Scenario::update_ts(timestep);
     }
 
     // grid means of rho, rho|u|, |Pi| that the last CM<2,OptimalAdapter> step used (the reference's d_moment_avg)

@@ -181,6 +181,32 @@ int lbm_get_moment_sums(lbm_handle* h, double sums[3]);
 
 int lbm_info(lbm_handle* h, lbm_info_t* out);
 
+/* ---- validation on the device --------------------------------------------------
+ * The sums the reference's Scenario::compute_error methods form on the host from h_u (src/core/lbm.cuh:163-171),
+ * taken on the device over this slab's rows in fp64 with a fixed summation order, so that a 32768^2 run is validated
+ * without moving 8.6 GB of velocities to the host.  All three need the macroscopics of the current step
+ * (lbm_step_with_macroscopics).  With several slabs the caller adds the per-slab results.
+ *   out[0] = sum |u - u_ref|^2, out[1] = sum |u_ref|^2; the reference's metric is 100*sqrt(out[0]/out[1])
+ *   (src/scenarios/taylorGreen/taylorGreenScenario.cuh:59-88). */
+int lbm_velocity_error_sums(lbm_handle* h, const float* d_u_ref_aos_local, double out[2]);
+/* Same against TaylorGreenValidation evaluated in place (src/scenarios/taylorGreen/taylorGreenFunctors.cuh:66-81);
+ * u0 = the functor's u_max/SCALE, t = Scenario::t. */
+int lbm_taylor_green_error_sums(lbm_handle* h, float nu, float u0, float t, double out[2]);
+/* Mean of u over x for every row of this slab (ny_local doubles each, host memory): the inner loop of
+ * PoiseuilleScenario::compute_error (src/scenarios/poiseuille/poiseuilleScenario.cuh:63-70). */
+int lbm_row_mean_velocity(lbm_handle* h, double* mean_ux_rows, double* mean_uy_rows);
+
+/* ---- checkpoint / restart (no reference counterpart) ------------------------------
+ * lbm_checkpoint_write stores the populations of this slab as they sit in HBM, the edge ring, the time step and the
+ * adapter means in one file (lbm_checkpoint_bytes long), streamed through pinned staging buffers; lbm_checkpoint_read
+ * restores them into a handle created with the same grid, slab decomposition and LBM_QK_D1_STALE_F0 setting.  Flags,
+ * bodies and forces are configuration: the caller sets them as for a fresh run.  The continued run is bit-identical
+ * to the uninterrupted one.  Both calls synchronise.  Peer-mapped slabs: every slab reads its file, then a host
+ * barrier, then the first step. */
+int lbm_checkpoint_bytes(lbm_handle* h, int64_t* out);
+int lbm_checkpoint_write(lbm_handle* h, const char* path);
+int lbm_checkpoint_read(lbm_handle* h, const char* path);
+
 /* ---- y-slab halo exchange (no reference counterpart) ----------------------------
  * Only the odd ("neighbour") steps of the in-place AA pattern touch the neighbour slab.  Before such a
  * step each rank needs 3*nx floats from each neighbour (lbm_halo_pack_pre on the owner ->
