@@ -30,6 +30,7 @@ SYMBOLS = [
     "lbm_host_alloc", "lbm_host_free",
     "lbm_velocity_error_sums", "lbm_taylor_green_error_sums", "lbm_row_mean_velocity",
     "lbm_checkpoint_bytes", "lbm_checkpoint_write", "lbm_checkpoint_read",
+    "lbm_ibm_exchange_floats", "lbm_ibm_pack", "lbm_ibm_unpack",
     "lbm_last_error",
 ]
 
@@ -38,7 +39,7 @@ class LbmConfig(C.Structure):
     _fields_ = [("nx", C.c_int32), ("ny", C.c_int32), ("periodic_x", C.c_int32), ("periodic_y", C.c_int32),
                 ("collision", C.c_int32), ("viscosity", C.c_float), ("S", C.c_float * 9), ("u_max", C.c_float),
                 ("force_x", C.c_float), ("force_y", C.c_float), ("quirks", C.c_int32), ("adapter_mode", C.c_int32),
-                ("device", C.c_int32), ("rank", C.c_int32), ("world", C.c_int32), ("reserved", C.c_int32 * 4)]
+                ("device", C.c_int32), ("rank", C.c_int32), ("world", C.c_int32), ("ibm_mailbox_nodes", C.c_int32), ("reserved", C.c_int32 * 3)]
 
 
 class LbmInfo(C.Structure):
@@ -112,6 +113,9 @@ def lib():
         "lbm_checkpoint_bytes": [vp, C.POINTER(C.c_int64)],
         "lbm_checkpoint_write": [vp, C.c_char_p],
         "lbm_checkpoint_read": [vp, C.c_char_p],
+        "lbm_ibm_exchange_floats": [vp, C.POINTER(C.c_int64)],
+        "lbm_ibm_pack": [vp, vp],
+        "lbm_ibm_unpack": [vp, vp],
     }
     for name, args in sig.items():
         fn = getattr(L, name)

@@ -56,7 +56,17 @@ struct lbm_handle {
     float* d_pts = nullptr; long long* ibm_nodes = nullptr; int* sten_idx = nullptr; float* sten_w = nullptr;
     int* csr_row = nullptr; int* csr_k = nullptr; float* csr_w = nullptr;
     float* ibm_rho = nullptr; float2* ibm_uprev = nullptr; float2* ibm_lagF = nullptr; float2* ibm_force = nullptr;
-    int np = 0, ibm_count = 0, ibm_ss = 4;
+    int np = 0, ibm_count = 0, ibm_ss = 4;       // markers / stencil nodes this slab works on (world > 1: the bodies it owns a node of)
+    // bodies across slab faces: every slab knows all bodies; node states travel through a mailbox indexed by the global node list
+    std::vector<int> body_start;                 // first marker of each body in h_pts
+    int np_total = 0;                            // markers of all bodies
+    long long nall = 0;                          // stencil nodes of all bodies (mailbox slots in use)
+    int mail_nodes = 0;                          // mailbox capacity in nodes (world > 1)
+    float* ibm_mail = nullptr;                   // inside the `pop` allocation, so the neighbours reach it through the same mapping
+    int* ibm_mail_idx = nullptr;
+    int ibm_mail_for_ts = -1;                    // halo-API coupling: the mailbox holds the all-reduced node states of this step
+    int nbrg_for_ts = -1;
+    std::vector<int> ibm_rows;                   // distinct rows of this slab's active stencil nodes (peer-coverage check)
     // general-path segments (kernels.cuh): mask per 128-cell segment + compact list, rebuilt lazily
     uint8_t* segmask = nullptr; int* gen_list = nullptr; int gen_count = 0; int nsx = 0; bool segs_dirty = true;
     // adapter
@@ -72,7 +82,8 @@ struct lbm_handle {
     // peer-mapped slab coupling (lbm_peer_export / lbm_peer_attach)
     unsigned long long* sync_flags = nullptr;      // 2 step counters written by the neighbours + padding, at the end of `pop`
     int* sync_timeout = nullptr;
-    struct Peer { float* base = nullptr; void* ipc_base = nullptr; long long plane = 0, off = 0; unsigned long long* flag = nullptr; bool attached = false; } peer[2];
+    struct Peer { float* base = nullptr; void* ipc_base = nullptr; long long plane = 0, off = 0; unsigned long long* flag = nullptr; bool attached = false;
+                  float* mail = nullptr; int y0 = 0, nyl = 0; } peer[2];
     cudaIpcMemHandle_t peer_ipc[2]{};
     bool direct() const { return peer[0].attached || peer[1].attached; }
 };
@@ -83,8 +94,9 @@ struct PeerDesc {
     long long pid;
     unsigned long long raw;         // device pointer, valid inside the exporting process
     long long plane;                // floats per slot plane
-    long long flags_off;            // byte offset of the two step counters inside the allocation
-    int nx, nyl, device, rank;
+    long long flags_off;            // byte offset of the step / IBM stage counters inside the allocation
+    long long mail_off;             // byte offset of the IBM mailbox inside the allocation
+    int nx, nyl, device, rank, y0, mail_nodes;
 };
 static_assert(sizeof(PeerDesc) <= LBM_PEER_DESC_BYTES, "PeerDesc must fit the ABI buffer");
 
@@ -143,7 +155,7 @@ extern "C" int lbm_destroy(lbm_handle* h) {
     for (int sd = 0; sd < 2; sd++)
         if (h->peer[sd].ipc_base && !(sd == 1 && h->peer[0].ipc_base == h->peer[1].ipc_base)) cudaIpcCloseMemHandle(h->peer[sd].ipc_base);
     void* ptrs[] = {h->sync_timeout, h->pop, h->flags, h->force_plane, h->ring, h->nbr_nodes, h->nbr_src, h->nbr_g, h->d_pts, h->ibm_nodes,
-                    h->sten_idx, h->sten_w, h->csr_row, h->csr_k, h->csr_w, h->ibm_rho, h->ibm_uprev, h->ibm_lagF, h->ibm_force,
+                    h->sten_idx, h->sten_w, h->csr_row, h->csr_k, h->csr_w, h->ibm_rho, h->ibm_uprev, h->ibm_lagF, h->ibm_force, h->ibm_mail_idx,
                     h->partials, h->stage, h->sums, h->avg, h->rho_out, h->u_out, h->mass_acc, h->segmask, h->gen_list, h->val_stage};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -183,16 +195,20 @@ extern "C" int lbm_create(const lbm_config* cfg, lbm_handle** out) {
     h->stream = h->own_stream;
     h->perim = 2 * cfg->nx + 2 * cfg->ny;
     const size_t pop_floats = h->plane * h->nplanes;
-    bool ok = dmalloc(h, &h->pop, pop_floats + 64) == cudaSuccess &&          // + 256 B: neighbour step counters (exported with the same IPC handle)
+    if (cfg->ibm_mailbox_nodes < 0) { cudaStreamDestroy(h->own_stream); delete h; return fail(LBM_ERR_INVALID, "ibm_mailbox_nodes < 0"); }
+    h->mail_nodes = cfg->world > 1 ? (cfg->ibm_mailbox_nodes > 0 ? cfg->ibm_mailbox_nodes : 65536) : 0;
+    const size_t tail_floats = 64 + (size_t)IBM_MAIL * h->mail_nodes;         // 256 B of neighbour counters + the IBM mailbox (exported with the same IPC handle)
+    bool ok = dmalloc(h, &h->pop, pop_floats + tail_floats) == cudaSuccess &&
               dmalloc(h, &h->sync_timeout, 1) == cudaSuccess &&
               dmalloc(h, &h->ring, (size_t)2 * h->perim * Q) == cudaSuccess &&
               dmalloc(h, &h->sums, 3) == cudaSuccess && dmalloc(h, &h->avg, 3) == cudaSuccess &&
               dmalloc(h, &h->mass_acc, 1) == cudaSuccess;
     if (ok && cfg->collision == LBM_CM_OPTIMAL) ok = dmalloc(h, &h->stage, (size_t)3 * RED_BLOCKS) == cudaSuccess;
     if (!ok) { std::string m = cudaGetErrorString(cudaGetLastError()); lbm_destroy(h); return fail(LBM_ERR_CUDA, "device allocation failed: " + m); }
-    cudaMemsetAsync(h->pop, 0, (pop_floats + 64) * sizeof(float), h->stream);
+    cudaMemsetAsync(h->pop, 0, (pop_floats + tail_floats) * sizeof(float), h->stream);
     cudaMemsetAsync(h->sync_timeout, 0, sizeof(int), h->stream);
-    h->sync_flags = reinterpret_cast<unsigned long long*>(h->pop + pop_floats);
+    h->sync_flags = reinterpret_cast<unsigned long long*>(h->pop + pop_floats);     // [0..1] step counters, [2..3] IBM stage counters
+    h->ibm_mail = h->mail_nodes ? h->pop + pop_floats + 64 : nullptr;
     cudaMemsetAsync(h->ring, 0, (size_t)2 * h->perim * Q * sizeof(float), h->stream);
     float one[3] = {1.f, 1.f, 1.f};
     cudaMemcpyAsync(h->avg, one, sizeof(one), cudaMemcpyHostToDevice, h->stream);
@@ -256,12 +272,10 @@ extern "C" int lbm_set_flags(lbm_handle* h, const int32_t* flags) {
         }
     if (h->nbr_nodes) { cudaFree(h->nbr_nodes); cudaFree(h->nbr_src); cudaFree(h->nbr_g); h->nbr_nodes = h->nbr_src = nullptr; h->nbr_g = nullptr; }
     h->nbr_count = (int)nbr.size();
-    if (any || h->np > 0) {
+    if (any || h->flags) {
         int rc = ensure_flags(h); if (rc) return rc;
         CU(cudaMemcpyAsync(h->flags, loc.data(), loc.size(), cudaMemcpyHostToDevice, h->stream));
         CU(cudaStreamSynchronize(h->stream));
-    } else if (h->flags) {
-        CU(cudaMemsetAsync(h->flags, 0, (size_t)h->nloc, h->stream));
     }
     if (h->nbr_count) {
         std::sort(nbr.begin(), nbr.end());
@@ -272,7 +286,7 @@ extern "C" int lbm_set_flags(lbm_handle* h, const int32_t* flags) {
         CU(cudaMemcpy(h->nbr_src, b.data(), b.size() * 8, cudaMemcpyHostToDevice));
     }
     h->segs_dirty = true;
-    if (h->np > 0) return rebuild_ibm(h);       // re-mark the IBM bit
+    if (!h->h_pts.empty()) return rebuild_ibm(h);       // re-mark the IBM bit
     return LBM_OK;
 }
 
@@ -303,10 +317,11 @@ extern "C" int lbm_set_force_field_device(lbm_handle* h, const float* d_force) {
 }
 
 // ------------------------------------------------------------------ IBM structure, built on the GPU
-__global__ void mark_ibm_kernel(uint8_t* flags, const long long* nodes, int n, long long node0, int set) {
+__global__ void mark_ibm_kernel(uint8_t* flags, const long long* nodes, int n, long long node0, long long nloc, int set) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     long long ln = nodes[i] - node0;
+    if (ln < 0 || ln >= nloc) return;               // a stencil node another slab owns
     if (set) flags[ln] |= FLAG_IBM; else flags[ln] &= (uint8_t)~FLAG_IBM;
 }
 __global__ void csr_fill_kernel(const int* order, const int* sten_idx_flat, const float* sten_w, int ss, int n, int* csr_k, float* csr_w) {
@@ -319,21 +334,80 @@ struct not_neg_i { __host__ __device__ bool operator()(int v) const { return v >
 struct fix_neg_slots { const long long* n; int* i; __device__ void operator()(int s) const { if (n[s] < 0) i[s] = -1; } };
 struct gather_idx { const int* idx; const int* ord; int* out; __device__ void operator()(int e) const { out[e] = idx[ord[e]]; } };
 
+// Several slabs: which bodies does this slab work on, and where do their nodes sit in the mailbox?  Host-side, O(markers).
+// Bodies whose stencils share a lattice node are coupled through the spreading sum and form one group; a slab works on
+// every group it owns a node of, with ALL markers of the group, so that each slab of a group computes the same bits.
+// The stencil node ids follow ibm_stencil_kernel exactly (same float arithmetic).
+static void select_bodies(lbm_handle* h, std::vector<float>& act_pts, std::vector<long long>& all_nodes) {
+    const bool two = (h->cfg.quirks & LBM_QK_D8_IBM_2X2) != 0;
+    const int w = two ? 2 : 4, lo = two ? 0 : -1, ss = w * w, nx = h->cfg.nx, ny = h->cfg.ny;
+    const int np = (int)(h->h_pts.size() / 2), nb = (int)h->body_start.size();
+    std::vector<long long> node((size_t)np * ss, -1);
+    for (int k = 0; k < np; k++) {
+        const float px = h->h_pts[2 * k], py = h->h_pts[2 * k + 1];
+        const float gx = floorf(px), gy = floorf(py);
+        for (int i = 0; i < w; i++)
+            for (int j = 0; j < w; j++) {
+                const int nxx = (int)(gx + (i + lo)), nyy = (int)(gy + (j + lo));
+                if (nxx >= nx || nxx < 0 || nyy >= ny || nyy < 0) continue;
+                node[(size_t)k * ss + i * w + j] = (long long)nyy * nx + nxx;
+            }
+    }
+    all_nodes.clear();
+    for (long long v : node) if (v >= 0) all_nodes.push_back(v);
+    std::sort(all_nodes.begin(), all_nodes.end());
+    all_nodes.erase(std::unique(all_nodes.begin(), all_nodes.end()), all_nodes.end());
+    // union-find over bodies through shared nodes
+    std::vector<int> parent(nb), first_body(all_nodes.size(), -1);
+    for (int b = 0; b < nb; b++) parent[b] = b;
+    auto find = [&](int b) { while (parent[b] != b) { parent[b] = parent[parent[b]]; b = parent[b]; } return b; };
+    auto body_end = [&](int b) { return b + 1 < nb ? h->body_start[b + 1] : np; };
+    for (int b = 0; b < nb; b++)
+        for (int k = h->body_start[b]; k < body_end(b); k++)
+            for (int sidx = 0; sidx < ss; sidx++) {
+                const long long v = node[(size_t)k * ss + sidx];
+                if (v < 0) continue;
+                const size_t i = std::lower_bound(all_nodes.begin(), all_nodes.end(), v) - all_nodes.begin();
+                if (first_body[i] < 0) first_body[i] = b; else parent[find(b)] = find(first_body[i]);
+            }
+    std::vector<char> owns(nb, 0);
+    for (size_t i = 0; i < all_nodes.size(); i++) {
+        const int y = (int)(all_nodes[i] / nx);
+        if (y >= h->y0 && y < h->y0 + h->nyl) owns[find(first_body[i])] = 1;
+    }
+    act_pts.clear();
+    for (int b = 0; b < nb; b++)
+        if (owns[find(b)]) act_pts.insert(act_pts.end(), h->h_pts.begin() + 2 * (size_t)h->body_start[b], h->h_pts.begin() + 2 * (size_t)body_end(b));
+}
+
 static int rebuild_ibm(lbm_handle* h) {
     CU(cudaSetDevice(h->cfg.device));
     h->segs_dirty = true;
-    if (h->cfg.world != 1) return fail(LBM_ERR_INVALID, "immersed bodies are supported on a single slab only (SURVEY.md 8e: cross-face stencils deferred)");
     auto pol = thrust::cuda::par.on(h->stream);
     if (h->ibm_nodes && h->flags && h->ibm_count) {
-        mark_ibm_kernel<<<(h->ibm_count + 255) / 256, 256, 0, h->stream>>>(h->flags, h->ibm_nodes, h->ibm_count, (long long)h->y0 * h->cfg.nx, 0);
+        mark_ibm_kernel<<<(h->ibm_count + 255) / 256, 256, 0, h->stream>>>(h->flags, h->ibm_nodes, h->ibm_count, (long long)h->y0 * h->cfg.nx, h->nloc, 0);
         h->launches++;
     }
-    void* old[] = {h->d_pts, h->ibm_nodes, h->sten_idx, h->sten_w, h->csr_row, h->csr_k, h->csr_w, h->ibm_rho, h->ibm_uprev, h->ibm_lagF, h->ibm_force};
+    void* old[] = {h->d_pts, h->ibm_nodes, h->sten_idx, h->sten_w, h->csr_row, h->csr_k, h->csr_w, h->ibm_rho, h->ibm_uprev, h->ibm_lagF, h->ibm_force, h->ibm_mail_idx};
     CU(cudaStreamSynchronize(h->stream));
     for (void* p : old) if (p) cudaFree(p);
     h->d_pts = nullptr; h->ibm_nodes = nullptr; h->sten_idx = nullptr; h->sten_w = nullptr; h->csr_row = nullptr; h->csr_k = nullptr; h->csr_w = nullptr;
-    h->ibm_rho = nullptr; h->ibm_uprev = nullptr; h->ibm_lagF = nullptr; h->ibm_force = nullptr;
-    h->np = (int)(h->h_pts.size() / 2); h->ibm_count = 0;
+    h->ibm_rho = nullptr; h->ibm_uprev = nullptr; h->ibm_lagF = nullptr; h->ibm_force = nullptr; h->ibm_mail_idx = nullptr;
+    h->np_total = (int)(h->h_pts.size() / 2);
+    h->np = 0; h->ibm_count = 0; h->nall = 0; h->ibm_rows.clear(); h->pre_for_ts = -1; h->ibm_mail_for_ts = -1;
+    if (h->np_total == 0) return LBM_OK;
+    // the markers this slab works on: all of them on a single slab, the bodies it owns a node of otherwise
+    std::vector<float> act_pts;
+    std::vector<long long> all_nodes;
+    const bool multi = h->cfg.world > 1;
+    if (multi) {
+        select_bodies(h, act_pts, all_nodes);
+        h->nall = (long long)all_nodes.size();
+        if (h->nall > h->mail_nodes)
+            return fail(LBM_ERR_INVALID, "the bodies touch " + std::to_string(h->nall) + " lattice nodes, more than the IBM mailbox holds (lbm_config.ibm_mailbox_nodes = " + std::to_string(h->mail_nodes) + ")");
+    }
+    const std::vector<float>& pts = multi ? act_pts : h->h_pts;
+    h->np = (int)(pts.size() / 2);
     if (h->np == 0) return LBM_OK;
     const int np = h->np;
     const bool two = (h->cfg.quirks & LBM_QK_D8_IBM_2X2) != 0;
@@ -342,7 +416,7 @@ static int rebuild_ibm(lbm_handle* h) {
     const int nslots = np * ss;
     long long* sten_node = nullptr; long long* keys = nullptr; int* order = nullptr; int* node_of = nullptr;
     CU(dmalloc(h, &h->d_pts, (size_t)2 * np));
-    CU(cudaMemcpyAsync(h->d_pts, h->h_pts.data(), (size_t)2 * np * 4, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->d_pts, pts.data(), (size_t)2 * np * 4, cudaMemcpyHostToDevice, h->stream));
     CU(cudaMalloc(&sten_node, (size_t)nslots * 8)); CU(cudaMalloc(&keys, (size_t)nslots * 8));
     CU(cudaMalloc(&order, (size_t)nslots * 4)); CU(cudaMalloc(&node_of, (size_t)nslots * 4));
     CU(dmalloc(h, &h->sten_w, (size_t)nslots)); CU(dmalloc(h, &h->sten_idx, (size_t)nslots));
@@ -381,8 +455,24 @@ static int rebuild_ibm(lbm_handle* h) {
     h->launches++;
     CU(dmalloc(h, &h->ibm_rho, (size_t)h->ibm_count)); CU(dmalloc(h, &h->ibm_uprev, (size_t)h->ibm_count));
     CU(dmalloc(h, &h->ibm_lagF, (size_t)np)); CU(dmalloc(h, &h->ibm_force, (size_t)h->ibm_count));
+    if (multi) {
+        // mailbox slot of every node of this slab's list = its rank in the global node list; rows for the peer-coverage check
+        std::vector<long long> mine((size_t)h->ibm_count);
+        CU(cudaMemcpyAsync(mine.data(), h->ibm_nodes, mine.size() * 8, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        std::vector<int> idx(mine.size());
+        for (size_t i = 0; i < mine.size(); i++) {
+            auto it = std::lower_bound(all_nodes.begin(), all_nodes.end(), mine[i]);
+            if (it == all_nodes.end() || *it != mine[i]) { cudaFree(sten_node); cudaFree(keys); cudaFree(order); cudaFree(node_of); return fail(LBM_ERR_STATE, "IBM: host and device stencil nodes disagree"); }
+            idx[i] = (int)(it - all_nodes.begin());
+            const int y = (int)(mine[i] / h->cfg.nx);
+            if (h->ibm_rows.empty() || h->ibm_rows.back() != y) h->ibm_rows.push_back(y);
+        }
+        CU(dmalloc(h, &h->ibm_mail_idx, idx.size()));
+        CU(cudaMemcpyAsync(h->ibm_mail_idx, idx.data(), idx.size() * 4, cudaMemcpyHostToDevice, h->stream));
+    }
     int rc = ensure_flags(h); if (rc) return rc;
-    mark_ibm_kernel<<<(h->ibm_count + 255) / 256, 256, 0, h->stream>>>(h->flags, h->ibm_nodes, h->ibm_count, (long long)h->y0 * h->cfg.nx, 1);
+    mark_ibm_kernel<<<(h->ibm_count + 255) / 256, 256, 0, h->stream>>>(h->flags, h->ibm_nodes, h->ibm_count, (long long)h->y0 * h->cfg.nx, h->nloc, 1);
     h->launches++;
     CU(cudaStreamSynchronize(h->stream));
     cudaFree(sten_node); cudaFree(keys); cudaFree(order); cudaFree(node_of);
@@ -392,8 +482,18 @@ static int rebuild_ibm(lbm_handle* h) {
 
 extern "C" int lbm_add_body(lbm_handle* h, const float* pts, int32_t n) {
     if (!h || (!pts && n > 0) || n < 0) return fail(LBM_ERR_INVALID, "bad body");
+    if (n == 0) return LBM_OK;
+    h->body_start.push_back((int)(h->h_pts.size() / 2));
     h->h_pts.insert(h->h_pts.end(), pts, pts + (size_t)2 * n);
-    return rebuild_ibm(h);
+    int rc = rebuild_ibm(h);
+    if (rc != LBM_OK) {         // leave the handle as it was before the call
+        h->h_pts.resize((size_t)2 * h->body_start.back());
+        h->body_start.pop_back();
+        const std::string keep = g_err;
+        rebuild_ibm(h);
+        g_err = keep;
+    }
+    return rc;
 }
 
 // ------------------------------------------------------------------ init
@@ -419,7 +519,8 @@ extern "C" int lbm_init_fields_device(lbm_handle* h, const float* d_rho, const f
     h->launches++;
     CU(cudaGetLastError());
     h->timestep = 0; h->macros_ts = 0; h->avg_for_ts = -1; h->pre_for_ts = -1;
-    CU(cudaMemsetAsync(h->sync_flags, 0, 16, h->stream));
+    CU(cudaMemsetAsync(h->sync_flags, 0, 32, h->stream));
+    h->ibm_mail_for_ts = -1; h->nbrg_for_ts = -1;
     return LBM_OK;
 }
 
@@ -448,7 +549,8 @@ extern "C" int lbm_init_taylor_green(lbm_handle* h, float nu, float u0) {
     h->launches++;
     CU(cudaGetLastError());
     h->timestep = 0; h->macros_ts = h->rho_out ? 0 : -1; h->avg_for_ts = -1; h->pre_for_ts = -1;
-    CU(cudaMemsetAsync(h->sync_flags, 0, 16, h->stream));
+    h->ibm_mail_for_ts = -1; h->nbrg_for_ts = -1;
+    CU(cudaMemsetAsync(h->sync_flags, 0, 32, h->stream));
     return LBM_OK;
 }
 
@@ -467,7 +569,7 @@ extern "C" int lbm_set_populations(lbm_handle* h, const float* f, const float* f
     h->launches++;
     CU(cudaStreamSynchronize(h->stream));
     cudaFree(df); cudaFree(dfb);
-    h->macros_ts = -1; h->avg_for_ts = -1; h->pre_for_ts = -1;
+    h->macros_ts = -1; h->avg_for_ts = -1; h->pre_for_ts = -1; h->ibm_mail_for_ts = -1; h->nbrg_for_ts = -1;
     return LBM_OK;
 }
 
@@ -553,21 +655,68 @@ static void launch_vec(lbm_handle* h, const Params& p) {
     default: { constexpr int COLL = C_CMOPT; constexpr bool ODD = ODDV; CALL; } break;      \
     }
 
+static IbmData ibm_data(lbm_handle* h) {
+    IbmData d{};
+    d.np = h->np; d.nnodes = h->ibm_count; d.ss = h->ibm_ss;
+    d.nodes = h->ibm_nodes; d.sten_idx = h->sten_idx; d.sten_w = h->sten_w; d.row = h->csr_row; d.csr_k = h->csr_k; d.csr_w = h->csr_w;
+    d.rho = h->ibm_rho; d.uprev = h->ibm_uprev; d.lagF = h->ibm_lagF; d.force = h->ibm_force;
+    d.mail_idx = h->ibm_mail_idx; d.mail = h->ibm_mail;
+    d.my_flags = h->sync_flags + 2; d.timed_out = h->sync_timeout;
+    for (int sd = 0; sd < 2; sd++) {
+        const bool on = h->peer[sd].attached && h->peer[sd].mail;
+        d.peer_mail[sd] = on ? h->peer[sd].mail : nullptr;
+        d.peer_flag[sd] = on ? h->peer[sd].flag + 2 : nullptr;
+        d.need[sd] = on ? 1 : 0;
+    }
+    return d;
+}
+
+static void launch_nbr_gather(lbm_handle* h, const Params& p, int t) {
+    if (h->nbrg_for_ts == t || !h->nbr_count) return;
+    if (t & 1) nbr_gather_kernel<true><<<(h->nbr_count + 127) / 128, 128, 0, h->stream>>>(p, h->nbr_src, h->nbr_g, h->nbr_count);
+    else nbr_gather_kernel<false><<<(h->nbr_count + 127) / 128, 128, 0, h->stream>>>(p, h->nbr_src, h->nbr_g, h->nbr_count);
+    h->launches++;
+    h->nbrg_for_ts = t;
+}
+
+// peer-mapped coupling: every stencil node this slab works on must belong to it or to an attached neighbour
+static int check_ibm_coverage(const lbm_handle* h) {
+    for (int y : h->ibm_rows) {
+        bool ok = y >= h->y0 && y < h->y0 + h->nyl;
+        for (int sd = 0; sd < 2 && !ok; sd++) ok = h->peer[sd].attached && y >= h->peer[sd].y0 && y < h->peer[sd].y0 + h->peer[sd].nyl;
+        if (!ok) return fail(LBM_ERR_INVALID, "a body (or a group of overlapping bodies) spans more than this slab and its two peer-mapped neighbours: use the halo coupling (lbm_ibm_pack / all-reduce / lbm_ibm_unpack)");
+    }
+    return LBM_OK;
+}
+
 // nbr gather + IBM (+ moments pre-pass) for step t; idempotent per timestep
 static int pre_passes(lbm_handle* h, int t, bool want_moments) {
     const bool odd = (t & 1) != 0;
     Params p = make_params(h, t);
     if (h->pre_for_ts != t) {
-        if (h->nbr_count) {
-            if (odd) nbr_gather_kernel<true><<<(h->nbr_count + 127) / 128, 128, 0, h->stream>>>(p, h->nbr_src, h->nbr_g, h->nbr_count);
-            else nbr_gather_kernel<false><<<(h->nbr_count + 127) / 128, 128, 0, h->stream>>>(p, h->nbr_src, h->nbr_g, h->nbr_count);
-            h->launches++;
-        }
-        if (h->ibm_count) {
-            IbmData d{h->np, h->ibm_count, h->ibm_ss, h->ibm_nodes, h->sten_idx, h->sten_w, h->csr_row, h->csr_k, h->csr_w,
-                      h->ibm_rho, h->ibm_uprev, h->ibm_lagF, h->ibm_force};
-            if (odd) ibm_kernel<true><<<1, 1024, 0, h->stream>>>(p, d); else ibm_kernel<false><<<1, 1024, 0, h->stream>>>(p, d);
-            h->launches++;
+        launch_nbr_gather(h, p, t);
+        if (h->cfg.world == 1) {
+            if (h->ibm_count) {
+                IbmData d = ibm_data(h);
+                if (odd) ibm_kernel<true><<<1, 1024, 0, h->stream>>>(p, d); else ibm_kernel<false><<<1, 1024, 0, h->stream>>>(p, d);
+                h->launches++;
+            }
+        } else if (h->np_total > 0) {
+            IbmData d = ibm_data(h);
+            if (h->direct()) {
+                // every slab posts its nodes (possibly none) and the stage counter; slabs that own part of a body then solve it
+                if (odd) ibm_gather_kernel<true><<<1, 1024, 0, h->stream>>>(p, d, h->ibm_mail, (unsigned long long)t);
+                else ibm_gather_kernel<false><<<1, 1024, 0, h->stream>>>(p, d, h->ibm_mail, (unsigned long long)t);
+                h->launches++;
+            } else {
+                if (h->ibm_count && h->ibm_mail_for_ts != t)
+                    return fail(LBM_ERR_STATE, "bodies on several slabs without peer-mapped neighbours: lbm_ibm_pack, all-reduce (sum) the buffer over the slabs, lbm_ibm_unpack before every lbm_step");
+                d.need[0] = d.need[1] = 0;
+            }
+            if (h->ibm_count) {
+                ibm_solve_kernel<<<1, 1024, 0, h->stream>>>(p, d, (unsigned long long)t);
+                h->launches++;
+            }
         }
         h->pre_for_ts = t;
     }
@@ -651,6 +800,41 @@ static int one_step(lbm_handle* h, bool want_macros) {
 
 static int prepare_resources(lbm_handle* h, bool want_macros);
 
+// ---- bodies across slab faces with the halo coupling (the peer-mapped coupling needs none of these)
+extern "C" int lbm_ibm_exchange_floats(lbm_handle* h, int64_t* out) {
+    if (!h || !out) return fail(LBM_ERR_INVALID, "NULL argument");
+    *out = (h->cfg.world > 1 && !h->direct()) ? (int64_t)IBM_MAIL * h->nall : 0;
+    return LBM_OK;
+}
+extern "C" int lbm_ibm_pack(lbm_handle* h, float* d_buf) {
+    if (!h || !d_buf) return fail(LBM_ERR_INVALID, "NULL argument");
+    if (h->cfg.world == 1 || h->nall == 0) return LBM_OK;
+    if (h->direct()) return fail(LBM_ERR_STATE, "peer-mapped slabs exchange the IBM node states themselves");
+    CU(cudaSetDevice(h->cfg.device));
+    const int t = h->timestep + 1;
+    Params p = make_params(h, t);
+    CU(cudaMemsetAsync(d_buf, 0, (size_t)IBM_MAIL * h->nall * sizeof(float), h->stream));      // nodes other slabs own: x + 0 = x in the all-reduce
+    launch_nbr_gather(h, p, t);
+    if (h->ibm_count) {
+        IbmData d = ibm_data(h);
+        d.peer_mail[0] = d.peer_mail[1] = nullptr; d.peer_flag[0] = d.peer_flag[1] = nullptr;
+        if (t & 1) ibm_gather_kernel<true><<<1, 1024, 0, h->stream>>>(p, d, d_buf, 0ull); else ibm_gather_kernel<false><<<1, 1024, 0, h->stream>>>(p, d, d_buf, 0ull);
+        h->launches++;
+    }
+    CU(cudaGetLastError());
+    return LBM_OK;
+}
+extern "C" int lbm_ibm_unpack(lbm_handle* h, const float* d_buf) {
+    if (!h || !d_buf) return fail(LBM_ERR_INVALID, "NULL argument");
+    if (h->cfg.world == 1 || h->nall == 0) return LBM_OK;
+    if (h->direct()) return fail(LBM_ERR_STATE, "peer-mapped slabs exchange the IBM node states themselves");
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaMemcpyAsync(h->ibm_mail, d_buf, (size_t)IBM_MAIL * h->nall * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+    h->ibm_mail_for_ts = h->timestep + 1;
+    h->pre_for_ts = -1;
+    return LBM_OK;
+}
+
 extern "C" int lbm_adapter_prepass(lbm_handle* h) {
     if (!h) return fail(LBM_ERR_INVALID, "NULL handle");
     if (h->cfg.collision != LBM_CM_OPTIMAL) return LBM_OK;
@@ -670,6 +854,7 @@ extern "C" int lbm_adapter_prepass(lbm_handle* h) {
 // process sits in cudaMalloc would dead-lock until the handshake timeout.
 static int prepare_resources(lbm_handle* h, bool want_macros) {
     int rc;
+    if (h->direct() && h->ibm_count) { rc = check_ibm_coverage(h); if (rc) return rc; }
     if (use_vec(h) && is_general(h)) { rc = ensure_segments(h); if (rc) return rc; }
     if (want_macros) { rc = ensure_macros(h); if (rc) return rc; }
     if (h->cfg.collision == LBM_CM_OPTIMAL) {
@@ -910,8 +1095,10 @@ static int checkpoint_io(lbm_handle* h, const char* path, bool save) {
     CU(cudaMemcpy(h->avg, k.avg, 12, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(h->sums, k.sums, 24, cudaMemcpyHostToDevice));
     // peer-mapped neighbours restart from the same step: all slabs must have loaded (host barrier) before any of them steps
-    unsigned long long fl[2] = {(unsigned long long)k.timestep, (unsigned long long)k.timestep};
-    CU(cudaMemcpy(h->sync_flags, fl, 16, cudaMemcpyHostToDevice));
+    const unsigned long long ts = (unsigned long long)k.timestep;
+    unsigned long long fl[4] = {ts, ts, ts, ts};
+    CU(cudaMemcpy(h->sync_flags, fl, 32, cudaMemcpyHostToDevice));
+    h->ibm_mail_for_ts = -1; h->nbrg_for_ts = -1;
     CU(cudaMemset(h->sync_timeout, 0, sizeof(int)));
     return LBM_OK;
 }
@@ -949,7 +1136,7 @@ extern "C" int lbm_info(lbm_handle* h, lbm_info_t* o) {
     if (!h || !o) return fail(LBM_ERR_INVALID, "NULL argument");
     memset(o, 0, sizeof(*o));
     o->nx = h->cfg.nx; o->ny = h->cfg.ny; o->y0 = h->y0; o->ny_local = h->nyl; o->rank = h->cfg.rank; o->world = h->cfg.world;
-    o->timestep = h->timestep; o->num_markers = h->np; o->num_ibm_nodes = h->ibm_count; o->num_neighbour_bc_nodes = h->nbr_count;
+    o->timestep = h->timestep; o->num_markers = h->np_total; o->num_ibm_nodes = h->ibm_count; o->num_neighbour_bc_nodes = h->nbr_count;
     o->device_bytes = h->bytes; o->bytes_per_cell = (double)h->bytes / (double)h->nloc; o->kernel_launches = h->launches;
     return LBM_OK;
 }
@@ -1020,7 +1207,8 @@ extern "C" int lbm_peer_export(lbm_handle* h, void* out) {
     CU(cudaIpcGetMemHandle(&d.ipc, h->pop));
     d.pid = (long long)getpid(); d.raw = (unsigned long long)(uintptr_t)h->pop; d.plane = (long long)h->plane;
     d.flags_off = (long long)((char*)h->sync_flags - (char*)h->pop);
-    d.nx = h->cfg.nx; d.nyl = h->nyl; d.device = h->cfg.device; d.rank = h->cfg.rank;
+    d.mail_off = h->ibm_mail ? (long long)((char*)h->ibm_mail - (char*)h->pop) : -1;
+    d.nx = h->cfg.nx; d.nyl = h->nyl; d.device = h->cfg.device; d.rank = h->cfg.rank; d.y0 = h->y0; d.mail_nodes = h->mail_nodes;
     memset(out, 0, LBM_PEER_DESC_BYTES);
     memcpy(out, &d, sizeof(d));
     return LBM_OK;
@@ -1033,6 +1221,7 @@ extern "C" int lbm_peer_attach(lbm_handle* h, int side, const void* desc) {
     CU(cudaStreamSynchronize(h->stream));
     PeerDesc d; memcpy(&d, desc, sizeof(d));
     if (d.nx != h->cfg.nx) return fail(LBM_ERR_INVALID, "neighbour slab has a different nx");
+    if (d.mail_nodes != h->mail_nodes) return fail(LBM_ERR_INVALID, "neighbour slab has a different ibm_mailbox_nodes");
     lbm_handle::Peer& P = h->peer[side];
     if (P.attached) return fail(LBM_ERR_STATE, "side already attached");
     char* base = nullptr;
@@ -1056,8 +1245,11 @@ extern "C" int lbm_peer_attach(lbm_handle* h, int side, const void* desc) {
     // side 0 (lower neighbour): its top edge row = local row nyl-1 -> plane row nyl; side 1: its local row 0 -> plane row 1
     P.off = (side == 0 ? (long long)d.nyl : 1ll) * d.nx;
     // I am the neighbour's upper peer when it is below me: it waits on its flags[1]
-    P.flag = reinterpret_cast<unsigned long long*>(base + d.flags_off) + (side == 0 ? 1 : 0);
+    P.flag = reinterpret_cast<unsigned long long*>(base + d.flags_off) + (side == 0 ? 1 : 0);     // its IBM stage counter: P.flag + 2
+    P.mail = d.mail_off >= 0 ? reinterpret_cast<float*>(base + d.mail_off) : nullptr;
+    P.y0 = d.y0; P.nyl = d.nyl;
     P.attached = true;
+    h->pre_for_ts = -1;
     return prepare_resources(h, false);
 }
 

@@ -513,30 +513,37 @@ struct IbmData {
     const int* row;                     // CSR node -> (marker, weight), markers ascending
     const int* csr_k; const float* csr_w;
     float* rho; float2* uprev; float2* lagF; float2* force;     // scratch + result
+    // bodies across slab faces: the node states travel through a mailbox indexed by the GLOBAL stencil-node list
+    // (IBM_MAIL floats per node), which every slab holds at the same offsets
+    const int* mail_idx;                // [nnodes] mailbox slot of each node of this slab's (active) list
+    float* mail;                        // this slab's mailbox
+    float* peer_mail[2];                // peer-mapped neighbours' mailboxes (nullptr = none): the owner of a node stores its state there too
+    unsigned long long* peer_flag[2];   // the neighbours' IBM stage counters this slab writes
+    volatile unsigned long long* my_flags;   // this slab's IBM stage counters [2], written by the lower / upper neighbour
+    int need[2];
+    int* timed_out;
 };
+constexpr int IBM_MAIL = 5;             // rho, u*_x, u*_y, F_x, F_y (d_force after reset_forces)
 
-// IBMManager<2>::multi_direct (src/IBM/IBMManager.cuh:222-252) as ONE launch working only on the nodes under
-// marker stencils: interpolate_velocities_kernel<2> (IBM_impl.cu:7-51), compute_lagrangian_kernel
-// (IBM_impl.cuh:9-26), spread_forces_kernel<2> (IBM_impl.cu:122-154; gather over a node<-marker CSR instead of
-// atomicAdd, so the sum order is fixed), correct_velocities_kernel + accumulate_forces_kernel (IBM_impl.cuh:30-68).
+// state of one stencil node before the IBM iterations: interpolate_velocities_kernel's inputs (IBM_impl.cu:7-51) and the
+// body force the result is accumulated onto (IBMManager.cuh:222-252)
 template <bool ODD>
-__global__ void __launch_bounds__(1024) ibm_kernel(const Params p, const IbmData d) {
+__device__ __forceinline__ void ibm_node_state(const Params& p, long long node, float& rho, float2& ustar, float2& F) {
+    const int x = (int)(node % p.nx), yl = (int)(node / p.nx) - p.y0;
+    float g[Q];
+    pull<ODD>(p, x, yl, g);
+    const long long ln = (long long)yl * p.nx + x;
+    const int bc = p.flags ? (p.flags[ln] & FLAG_MASK) : 0;
+    if (bc) apply_bc(p, bc, g, x, p.y0 + yl);
+    const Moments m = moments(g);
+    rho = m.rho;
+    ustar = make_float2(m.ux, m.uy);                        // the uncorrected u* (IBMManager.cuh:227)
+    F = p.force_plane ? p.force_plane[ln] : make_float2(p.fx, p.fy);     // d_force after reset_forces, before accumulation
+}
+
+// 3 iterations of interpolate -> Lagrangian force -> spread -> correct -> accumulate over d.rho / d.uprev / d.force (one block)
+__device__ __forceinline__ void ibm_iterations(const Params& p, const IbmData& d) {
     const bool clip = (p.quirks & QK_D7) != 0;
-    for (int i = threadIdx.x; i < d.nnodes; i += blockDim.x) {
-        long long node = d.nodes[i];
-        int x = (int)(node % p.nx), yl = (int)(node / p.nx) - p.y0;
-        float g[Q];
-        pull<ODD>(p, x, yl, g);
-        const long long ln = (long long)yl * p.nx + x;
-        int bc = p.flags ? (p.flags[ln] & FLAG_MASK) : 0;
-        if (bc) apply_bc(p, bc, g, x, p.y0 + yl);
-        Moments m = moments(g);
-        d.rho[i] = m.rho;
-        d.uprev[i] = make_float2(m.ux, m.uy);               // the uncorrected u* (IBMManager.cuh:227)
-        float2 F = p.force_plane ? p.force_plane[ln] : make_float2(p.fx, p.fy);
-        d.force[i] = F;                                     // d_force after reset_forces, before accumulation
-    }
-    __syncthreads();
     for (int iter = 0; iter < 3; iter++) {                  // ITER_MAX (IBMManager.cuh:8)
         for (int k = threadIdx.x; k < d.np; k += blockDim.x) {
             float rho = 0.f, ux = 0.f, uy = 0.f;
@@ -565,6 +572,73 @@ __global__ void __launch_bounds__(1024) ibm_kernel(const Params p, const IbmData
         }
         __syncthreads();
     }
+}
+
+// IBMManager<2>::multi_direct (src/IBM/IBMManager.cuh:222-252) as ONE launch working only on the nodes under
+// marker stencils: interpolate_velocities_kernel<2> (IBM_impl.cu:7-51), compute_lagrangian_kernel
+// (IBM_impl.cuh:9-26), spread_forces_kernel<2> (IBM_impl.cu:122-154; gather over a node<-marker CSR instead of
+// atomicAdd, so the sum order is fixed), correct_velocities_kernel + accumulate_forces_kernel (IBM_impl.cuh:30-68).
+template <bool ODD>
+__global__ void __launch_bounds__(1024) ibm_kernel(const Params p, const IbmData d) {
+    for (int i = threadIdx.x; i < d.nnodes; i += blockDim.x) {
+        float rho; float2 us, F;
+        ibm_node_state<ODD>(p, d.nodes[i], rho, us, F);
+        d.rho[i] = rho; d.uprev[i] = us; d.force[i] = F;
+    }
+    __syncthreads();
+    ibm_iterations(p, d);
+}
+
+// Bodies whose stencils cross a slab face.  Stage 1, on every slab: the states of the stencil nodes
+// THIS slab owns go into mailbox `out` (its own, or a caller's buffer that is then all-reduced) and, peer-mapped, into the
+// neighbours' mailboxes over NVLink, followed by the stage counter t.
+template <bool ODD>
+__global__ void __launch_bounds__(1024) ibm_gather_kernel(const Params p, const IbmData d, float* out, unsigned long long t) {
+    for (int i = threadIdx.x; i < d.nnodes; i += blockDim.x) {
+        const long long node = d.nodes[i];
+        const int yg = (int)(node / p.nx);
+        if (yg < p.y0 || yg >= p.y0 + p.nyl) continue;
+        float rho; float2 us, F;
+        ibm_node_state<ODD>(p, node, rho, us, F);
+        const float v[IBM_MAIL] = {rho, us.x, us.y, F.x, F.y};
+        const long long o = (long long)d.mail_idx[i] * IBM_MAIL;
+#pragma unroll
+        for (int c = 0; c < IBM_MAIL; c++) {
+            out[o + c] = v[c];
+            if (d.peer_mail[0]) d.peer_mail[0][o + c] = v[c];
+            if (d.peer_mail[1]) d.peer_mail[1][o + c] = v[c];
+        }
+    }
+    if (d.peer_flag[0] || d.peer_flag[1]) {
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (d.peer_flag[0]) *(volatile unsigned long long*)d.peer_flag[0] = t;
+            if (d.peer_flag[1]) *(volatile unsigned long long*)d.peer_flag[1] = t;
+            __threadfence_system();
+        }
+    }
+}
+// Stage 2, on every slab that owns part of a body: wait for the neighbours' stage counters (peer-mapped only), read the
+// complete node states from the mailbox and run the iterations redundantly — every slab of a body computes the same bits.
+__global__ void __launch_bounds__(1024) ibm_solve_kernel(const Params p, const IbmData d, unsigned long long t) {
+    if ((d.need[0] || d.need[1]) && threadIdx.x == 0) {
+        const long long t0 = clock64();
+        while ((d.need[0] && d.my_flags[0] < t) || (d.need[1] && d.my_flags[1] < t)) {
+            if (clock64() - t0 > 20000000000ll) { *d.timed_out = 1; break; }
+            __nanosleep(200);
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < d.nnodes; i += blockDim.x) {
+        const float* m = d.mail + (long long)d.mail_idx[i] * IBM_MAIL;
+        d.rho[i] = __ldcv(m);
+        d.uprev[i] = make_float2(__ldcv(m + 1), __ldcv(m + 2));
+        d.force[i] = make_float2(__ldcv(m + 3), __ldcv(m + 4));
+    }
+    __syncthreads();
+    ibm_iterations(p, d);
 }
 
 // delta4 / kernel2D — reference src/IBM/IBMUtils.cuh:23-43

@@ -4,8 +4,9 @@ One process per GPU (torchrun); slab g owns rows [y0, y0+ny_local).  The in-plac
 the neighbour slab only on odd steps: before such a step a rank needs, per face, the three
 populations of the neighbour's edge row that stream into it (3*nx floats), and after it the three
 populations it wrote for the neighbour travel back.  torch.distributed (NCCL over NVLink on the
-GPU box, gloo in the CPU tests) moves those rows; everything else is local.  The only other
-collective is the 3-double all-reduce of CM<2,OptimalAdapter>'s grid sums.
+GPU box, gloo in the CPU tests) moves those rows; everything else is local.  The other collectives
+are the 3-double all-reduce of CM<2,OptimalAdapter>'s grid sums and, when immersed bodies are present,
+the all-reduce of the stencil-node states (5 floats per node touched by a marker; lbm_ibm_pack/unpack).
 
 The engine is passed in as an object with the halo/step methods of cuda_lbm_b200.solver.Engine so that
 the exchange schedule can be tested on CPU with a stand-in (tests/test_slab_gloo.py).
@@ -98,6 +99,8 @@ class SlabSolver:
         self.optimal, self.exact = optimal_adapter, adapter_exact
         self.group = group
         self._sums = torch.zeros(3, dtype=torch.float64, device=device)
+        self._device = device
+        self._ibm = None            # exchange buffer of the IBM node states, sized at the first step (bodies are added after construction)
         self.collectives = 0
         self.mode = mode if self.world > 1 else "single"
         if self.mode == "direct":
@@ -115,6 +118,19 @@ class SlabSolver:
         self.e.set_moment_sums(s.cpu().tolist())
         self.collectives += 1
 
+    def _exchange_ibm(self):
+        """Bodies across slab faces, halo coupling: every slab contributes the states of the stencil nodes it owns (zeros
+        elsewhere), so the sum over slabs is a gather — bit-exact, whatever order the all-reduce adds in."""
+        if self._ibm is None:
+            nf = getattr(self.e, "ibm_exchange_floats", lambda: 0)()
+            self._ibm = torch.zeros(nf, dtype=torch.float32, device=self._device)
+        if self._ibm.numel() == 0:
+            return
+        self.e.ibm_pack(self._ibm.data_ptr())
+        dist.all_reduce(self._ibm, group=self.group)
+        self.e.ibm_unpack(self._ibm.data_ptr())
+        self.collectives += 1
+
     def step(self, n=1, macroscopics=False):
         if self.world == 1 or (self.mode == "direct" and not self.optimal):
             self.e.step(n, macroscopics=macroscopics)
@@ -123,6 +139,8 @@ class SlabSolver:
             need = self.e.next_step_needs_halo()
             if need:
                 self.x.exchange("pre")
+            if self.mode != "direct":
+                self._exchange_ibm()
             if self.optimal and self.exact:
                 self.e.adapter_prepass()
                 self._allreduce_sums()

@@ -31,7 +31,8 @@ def default_S(collision, omega):
 
 class Engine:
     def __init__(self, nx, ny, collision=capi.BGK, viscosity=1.0 / 6.0, S=None, periodic=(True, True), u_max=0.1,
-                 force=(0.0, 0.0), quirks=capi.QK_REFERENCE, adapter_mode=capi.ADAPTER_EXACT, device=0, rank=0, world=1):
+                 force=(0.0, 0.0), quirks=capi.QK_REFERENCE, adapter_mode=capi.ADAPTER_EXACT, device=0, rank=0, world=1,
+                 ibm_mailbox_nodes=0):
         L = lib()
         cfg = LbmConfig()
         check(L.lbm_default_config(C.byref(cfg)))
@@ -49,6 +50,7 @@ class Engine:
         cfg.force_x, cfg.force_y = float(np.float32(force[0])), float(np.float32(force[1]))
         cfg.quirks, cfg.adapter_mode = quirks, adapter_mode
         cfg.device, cfg.rank, cfg.world = device, rank, world
+        cfg.ibm_mailbox_nodes = ibm_mailbox_nodes
         self.cfg = cfg
         self._h = C.c_void_p()
         check(L.lbm_create(C.byref(cfg), C.byref(self._h)))
@@ -196,6 +198,18 @@ class Engine:
 
     def peer_detach(self):
         check(lib().lbm_peer_detach(self._h))
+
+    # --- bodies across slab faces, halo coupling (device pointers as ints) ---
+    def ibm_exchange_floats(self):
+        n = C.c_int64()
+        check(lib().lbm_ibm_exchange_floats(self._h, C.byref(n)))
+        return n.value
+
+    def ibm_pack(self, ptr):
+        check(lib().lbm_ibm_pack(self._h, C.c_void_p(ptr)))
+
+    def ibm_unpack(self, ptr):
+        check(lib().lbm_ibm_unpack(self._h, C.c_void_p(ptr)))
 
     # --- slab halos (device pointers as ints) ---
     def next_step_needs_halo(self):

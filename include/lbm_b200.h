@@ -80,7 +80,8 @@ typedef struct lbm_config {
     int32_t adapter_mode;       /* LBM_ADAPTER_* (only read for LBM_CM_OPTIMAL) */
     int32_t device;             /* CUDA device ordinal */
     int32_t rank, world;        /* y-slab index and slab count (1 = whole domain on this GPU) */
-    int32_t reserved[4];        /* must be zero */
+    int32_t ibm_mailbox_nodes;  /* world > 1: capacity of the IBM node mailbox in lattice nodes (0 = 65536; 20 B each) */
+    int32_t reserved[3];        /* must be zero */
 } lbm_config;
 
 typedef struct lbm_info_t {
@@ -124,7 +125,9 @@ int lbm_set_body_force(lbm_handle* h, float fx, float fy);
 
 /* Scenario::add_bodies() + IBMManager<2>::init_and_dispatch — src/IBM/IBMManager.cuh:54-109.
  * points = IBMBody::points, AoS [i*2+c], host memory, global lattice coordinates.  The marker->node
- * stencil structure is built on the GPU.  The caller keeps ownership of `points`. */
+ * stencil structure is built on the GPU.  The caller keeps ownership of `points`.  One call per body, any number of
+ * bodies.  With several slabs EVERY slab is given EVERY body, in the same order: a slab works on the bodies whose
+ * stencils reach into its rows (bodies that share lattice nodes count as one) and ignores the rest. */
 int lbm_add_body(lbm_handle* h, const float* points_aos, int32_t num_points);
 
 /* LBM<2>::init<Scenario>() — src/core/init/init.cuh:45-86: rho,u = the Init functor evaluated for every
@@ -219,6 +222,19 @@ int lbm_halo_pack_pre(lbm_handle* h, int side, float* d_buf);
 int lbm_halo_unpack_pre(lbm_handle* h, int side, const float* d_buf);
 int lbm_halo_pack_post(lbm_handle* h, int side, float* d_buf);
 int lbm_halo_unpack_post(lbm_handle* h, int side, const float* d_buf);
+
+/* ---- bodies whose stencils cross a slab face (no reference counterpart) -------------------
+ * Every slab that owns part of a body runs the three direct-forcing iterations for the WHOLE body, redundantly and
+ * with identical bits, on the states (rho, u*, F) of all its stencil nodes; each state is computed by the slab that
+ * owns the node.  With the halo coupling the states travel like the halo rows: lbm_ibm_pack writes this slab's node
+ * states for the NEXT step into a device buffer of lbm_ibm_exchange_floats floats (zeros for nodes other slabs own),
+ * the caller all-reduces (sum) the buffer over ALL slabs, lbm_ibm_unpack hands it back, then lbm_step.  (After the
+ * pre-step halo exchange; before lbm_adapter_prepass.)  With peer-mapped neighbours none of this is needed: the owners
+ * store the states into their neighbours' mailboxes over NVLink inside the pre-pass kernel — a body may then span a
+ * slab and its two neighbours, not more.  lbm_ibm_exchange_floats is 0 when nothing has to be exchanged. */
+int lbm_ibm_exchange_floats(lbm_handle* h, int64_t* out);
+int lbm_ibm_pack(lbm_handle* h, float* d_buf);
+int lbm_ibm_unpack(lbm_handle* h, const float* d_buf);
 
 /* ---- peer-mapped neighbours: halo rows without copies (no reference counterpart; SURVEY.md §5, §8e option 1) --------
  * Each slab exports a descriptor of its population buffer (a CUDA IPC handle when the neighbour lives in another

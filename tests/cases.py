@@ -70,6 +70,9 @@ class Case:
         return f32(3.0) * D, f32(self.ny / 2.0), D / f32(2.0)
 
     def markers(self):
+        """IBMBody::points of the case's bodies: one [n,2] array, or a list of them (one lbm_add_body call each)."""
+        if getattr(self, "bodies", None) is not None:
+            return self.bodies
         if self.kind != "cyl_ibm":
             return None
         from oracle import oracle as O
@@ -119,7 +122,7 @@ def make_oracle(case, quirks=63):
     o.set_flags(case.flags())
     m = case.markers()
     if m is not None:
-        o.set_markers(m)
+        o.set_markers(np.concatenate(m, axis=0) if isinstance(m, list) else m)     # the reference keeps one marker array for all bodies (IBMManager.cuh:54-109)
     return o
 
 
@@ -130,7 +133,8 @@ def make_engine(case, quirks=63, adapter_mode=0, **kw):
     e.set_flags(case.flags())
     m = case.markers()
     if m is not None:
-        e.add_body(m)
+        for body in (m if isinstance(m, list) else [m]):
+            e.add_body(body)
     return e
 
 

@@ -159,6 +159,23 @@ def _run_slabs(case, world, nsteps, adapter_mode=0, direct=False, chunk=1):
         for e in engs:
             e.sync()
 
+    ibm_floats = engs[0].ibm_exchange_floats()
+    ibm_bufs = [torch.zeros(max(1, ibm_floats), dtype=torch.float32, device="cuda") for _ in engs]
+
+    def exchange_ibm():
+        """what slab.py does with dist.all_reduce: every slab packs the node states it owns, all receive the sum"""
+        if not ibm_floats:
+            return
+        for e, b in zip(engs, ibm_bufs):
+            e.ibm_pack(b.data_ptr())
+        for e in engs:
+            e.sync()
+        total = torch.stack(ibm_bufs).sum(dim=0)
+        for e in engs:
+            e.ibm_unpack(total.data_ptr())
+        for e in engs:
+            e.sync()
+
     if direct and case.coll != cases.CM_OPT:
         done = 0
         while done < nsteps:
@@ -173,6 +190,7 @@ def _run_slabs(case, world, nsteps, adapter_mode=0, direct=False, chunk=1):
         need = engs[0].next_step_needs_halo()
         if need:
             exchange("pre")
+        exchange_ibm()
         if case.coll == cases.CM_OPT:
             if adapter_mode == 0:
                 for e in engs:

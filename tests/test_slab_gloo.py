@@ -21,8 +21,9 @@ NX = 16
 
 
 class FakeEngine:
-    def __init__(self, rank, world):
+    def __init__(self, rank, world, ibm_floats=0):
         self.rank, self.world, self.t = rank, world, 0
+        self.ibm_floats, self.ibm_log = ibm_floats, []
         self.log = []          # (step, phase, side, received tag)
         self.sums = np.array([1.0 + rank, 2.0, 3.0])
         self.set_sums = []
@@ -55,14 +56,32 @@ class FakeEngine:
     def adapter_prepass(self):
         pass
 
+    # bodies across slab faces: slab r "owns" every world-th node state, the rest of its buffer is zero
+    def ibm_exchange_floats(self):
+        return self.ibm_floats
 
-def _worker(rank, world, port, periodic, optimal, q):
+    def _ibm_buf(self, ptr):
+        return np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_float)), shape=(self.ibm_floats,))
+
+    def ibm_pack(self, ptr):
+        b = self._ibm_buf(ptr)
+        b[:] = 0
+        b[self.rank::self.world] = 100 * (self.rank + 1) + self.t
+
+    def ibm_unpack(self, ptr):
+        self.ibm_log.append((self.t, self._ibm_buf(ptr).copy()))
+
+
+def _worker(rank, world, port, periodic, optimal, q, ibm_floats=0):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    e = FakeEngine(rank, world)
+    e = FakeEngine(rank, world, ibm_floats)
     s = SlabSolver(e, NX, periodic, torch.device("cpu"), optimal_adapter=optimal, adapter_exact=True)
     s.step(4)
-    q.put((rank, e.log, e.set_sums, s.collectives))
+    if ibm_floats:
+        q.put((rank, e.ibm_log, None, s.collectives))
+    else:
+        q.put((rank, e.log, e.set_sums, s.collectives))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -73,11 +92,11 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _run(world, periodic, optimal=False):
+def _run(world, periodic, optimal=False, ibm_floats=0):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    ps = [ctx.Process(target=_worker, args=(r, world, port, periodic, optimal, q)) for r in range(world)]
+    ps = [ctx.Process(target=_worker, args=(r, world, port, periodic, optimal, q, ibm_floats)) for r in range(world)]
     for p in ps:
         p.start()
     res = {}
@@ -114,6 +133,21 @@ def test_optimal_adapter_allreduce_every_step():
     for rank, (_, sums, ncoll) in res.items():
         assert ncoll == 4 and len(sums) == 4
         assert sums[0] == [3.0, 4.0, 6.0]        # (1+0)+(1+1), 2+2, 3+3
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_ibm_node_states_are_gathered_by_allreduce_every_step(world):
+    """Bodies across slab faces with the halo coupling: before EVERY step each slab packs the node states it owns (zeros
+    elsewhere), the sum over slabs hands every slab the complete set, bit for bit (x + 0 = x)."""
+    nf = 10
+    res = _run(world, False, ibm_floats=nf)
+    for rank, (log, _, ncoll) in res.items():
+        assert ncoll == 4 and [t for t, _ in log] == [0, 1, 2, 3]
+        for t, got in log:
+            want = np.zeros(nf, np.float32)
+            for r in range(world):
+                want[r::world] = 100 * (r + 1) + t
+            assert np.array_equal(got, want), (rank, t, got, want)
 
 
 def test_slab_rows_cover_the_grid():
