@@ -45,6 +45,9 @@ struct lbm_handle {
     long long nloc = 0;
     size_t plane = 0;               // floats per slot plane
     cudaStream_t stream = nullptr, own_stream = nullptr;
+    // the general-path work of a step (IBM pre-pass, boundary / body segments) runs beside the vectorised kernel on a second
+    // stream: under the AA pattern a cell reads exactly the slots it overwrites, so the two kernels touch disjoint memory
+    cudaStream_t side_stream = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr; bool overlap = true;
     float* pop = nullptr;           // 9 (+1) planes
     int nplanes = 9;
     uint8_t* flags = nullptr;
@@ -130,6 +133,29 @@ static Params make_params(lbm_handle* h, int t) {
     return p;
 }
 
+// CUDA loads kernels lazily, at their first launch, and that load waits for the device to drain.  A first launch issued while
+// a handshake kernel of another handle in this process spins would therefore dead-lock until the handshake timeout
+// (seen on a B200: two peer-mapped slabs in one process, 7 steps enqueued at once).  Every kernel a step can launch is
+// loaded up front instead, once per device, before any handle exists.
+template <typename K> static void preload(K kernel) { cudaFuncAttributes a; cudaFuncGetAttributes(&a, kernel); }
+template <int COLL> static void preload_coll() {
+    preload(step_vec_kernel<COLL, false>); preload(step_vec_kernel<COLL, true>);
+    preload(step_kernel<COLL, false, false>); preload(step_kernel<COLL, false, true>);
+    preload(step_kernel<COLL, true, false>); preload(step_kernel<COLL, true, true>);
+}
+static void preload_kernels(int device) {
+    static bool done[64] = {};
+    if (device < 0 || device >= 64 || done[device]) return;
+    done[device] = true;
+    preload_coll<C_BGK>(); preload_coll<C_MRT>(); preload_coll<C_CM>(); preload_coll<C_CMOPT>();
+    preload(moments_kernel<false>); preload(moments_kernel<true>); preload(moments_vec_kernel<false>); preload(moments_vec_kernel<true>);
+    preload(reduce_stage1_kernel); preload(reduce_stage2_kernel); preload(sums_to_avg_kernel);
+    preload(nbr_gather_kernel<false>); preload(nbr_gather_kernel<true>);
+    preload(ibm_kernel<false>); preload(ibm_kernel<true>); preload(ibm_gather_kernel<false>); preload(ibm_gather_kernel<true>); preload(ibm_solve_kernel);
+    preload(wait_neighbours_kernel); preload(signal_neighbours_kernel); preload(build_segmask_kernel);
+    cudaGetLastError();
+}
+
 static dim3 grid_of(const lbm_handle* h) { return dim3((h->cfg.nx + BX - 1) / BX, h->nyl); }
 
 extern "C" const char* lbm_last_error(void) { return g_err.c_str(); }
@@ -159,6 +185,9 @@ extern "C" int lbm_destroy(lbm_handle* h) {
                     h->partials, h->stage, h->sums, h->avg, h->rho_out, h->u_out, h->mass_acc, h->segmask, h->gen_list, h->val_stage};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    if (h->side_stream) cudaStreamDestroy(h->side_stream);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
     delete h;
     return LBM_OK;
 }
@@ -178,6 +207,7 @@ extern "C" int lbm_create(const lbm_config* cfg, lbm_handle** out) {
     CU(cudaGetDeviceCount(&ndev));
     if (cfg->device < 0 || cfg->device >= ndev) return fail(LBM_ERR_INVALID, "no such CUDA device");
     CU(cudaSetDevice(cfg->device));
+    preload_kernels(cfg->device);
     lbm_handle* h = new lbm_handle();
     h->cfg = *cfg;
     const float tau = 3 * cfg->viscosity + 0.5f;     // viscosity_to_tau, lbm_constants.cuh:365-367
@@ -193,6 +223,15 @@ extern "C" int lbm_create(const lbm_config* cfg, lbm_handle** out) {
     cudaError_t e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete h; return fail(LBM_ERR_CUDA, cudaGetErrorString(e)); }
     h->stream = h->own_stream;
+    {   // LBM_B200_OVERLAP=0 serialises the general-path kernels behind the vectorised one (diagnosis / A-B timing)
+        const char* ov = getenv("LBM_B200_OVERLAP");
+        h->overlap = !(ov && ov[0] == '0');
+        if (h->overlap && (cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking) != cudaSuccess ||
+                           cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+                           cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess)) {
+            std::string m = cudaGetErrorString(cudaGetLastError()); lbm_destroy(h); return fail(LBM_ERR_CUDA, "stream / event creation failed: " + m);
+        }
+    }
     h->perim = 2 * cfg->nx + 2 * cfg->ny;
     const size_t pop_floats = h->plane * h->nplanes;
     if (cfg->ibm_mailbox_nodes < 0) { cudaStreamDestroy(h->own_stream); delete h; return fail(LBM_ERR_INVALID, "ibm_mailbox_nodes < 0"); }
@@ -753,6 +792,21 @@ static int pre_passes(lbm_handle* h, int t, bool want_moments) {
     return LBM_OK;
 }
 
+// fork: work enqueued on h->stream from here on runs on the side stream, after everything enqueued on the main stream so far
+static int fork_side(lbm_handle* h, cudaStream_t main) {
+    CU(cudaEventRecord(h->ev_fork, main));
+    CU(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
+    h->stream = h->side_stream;
+    return LBM_OK;
+}
+// join: back to the main stream, which waits for the side stream's work
+static int join_side(lbm_handle* h, cudaStream_t main) {
+    h->stream = main;
+    CU(cudaEventRecord(h->ev_join, h->side_stream));
+    CU(cudaStreamWaitEvent(main, h->ev_join, 0));
+    return LBM_OK;
+}
+
 static int one_step(lbm_handle* h, bool want_macros) {
     const int t = h->timestep + 1;
     const bool odd = (t & 1) != 0;
@@ -761,10 +815,24 @@ static int one_step(lbm_handle* h, bool want_macros) {
     const bool need_moments = opt && h->avg_for_ts != t;
     if (need_moments && h->cfg.world > 1)
         return fail(LBM_ERR_STATE, "OptimalAdapter on several slabs: call lbm_adapter_prepass, all-reduce lbm_get_moment_sums, lbm_set_moment_sums before lbm_step");
-    int rc = pre_passes(h, t, need_moments); if (rc) return rc;
+    int rc;
+    cudaStream_t main = h->stream;
+    if (use_vec(h) && general) { rc = ensure_segments(h); if (rc) return rc; }
+    const int ngen = (use_vec(h) && general) ? h->gen_count : 0;
+    // two kernels side by side: the vectorised one on the main stream, pre-passes + general segments on the side stream
+    const bool side = h->overlap && ngen > 0;
+    bool forked = false;
+    if (side && !need_moments) {
+        // the neighbour-BC gather reads cells the vectorised kernel overwrites: it stays in front of the fork
+        launch_nbr_gather(h, make_params(h, t), t);
+        rc = fork_side(h, main); if (rc) return rc;
+        forked = true;
+    }
+    rc = pre_passes(h, t, need_moments);
+    if (rc) { h->stream = main; return rc; }
     Params p = make_params(h, t);
     const bool lagged = opt && h->cfg.adapter_mode == LBM_ADAPTER_LAGGED;
-    if (want_macros) { rc = ensure_macros(h); if (rc) return rc; p.rho_out = h->rho_out; p.u_out = h->u_out; }
+    if (want_macros) { rc = ensure_macros(h); if (rc) { h->stream = main; return rc; } p.rho_out = h->rho_out; p.u_out = h->u_out; }
     long long nparts = 0;
     if (!use_vec(h)) {
         // nx not a multiple of 4: the scalar kernel covers the whole slab
@@ -773,21 +841,22 @@ static int one_step(lbm_handle* h, bool want_macros) {
         if (odd) { DISPATCH_COLL(true, (launch_scalar<COLL, ODD>(h, p, general, g))) } else { DISPATCH_COLL(false, (launch_scalar<COLL, ODD>(h, p, general, g))) }
         h->launches++;
     } else {
-        if (general) { rc = ensure_segments(h); if (rc) return rc; }
-        const int ngen = general ? h->gen_count : 0;
         int threads; dim3 gv = vec_grid(h, threads);
         const long long nvb = (long long)gv.x * gv.y;
-        if (lagged) { nparts = nvb + ngen; rc = ensure_partials(h, nparts); if (rc) return rc; p.partials = h->partials; }
-        if (general) p.segmask = h->segmask;
-        if (odd) { DISPATCH_COLL(true, (launch_vec<COLL, ODD>(h, p))) } else { DISPATCH_COLL(false, (launch_vec<COLL, ODD>(h, p))) }
-        h->launches++;
+        if (lagged) { nparts = nvb + ngen; rc = ensure_partials(h, nparts); if (rc) { h->stream = main; return rc; } p.partials = h->partials; }
         if (ngen > 0) {
+            if (side && !forked) { rc = fork_side(h, main); if (rc) return rc; forked = true; }      // the moments pre-pass came first, on the main stream
             Params pg = p; pg.segmask = nullptr; pg.gen_list = h->gen_list;
             if (lagged) pg.partials = h->partials + 3 * nvb;
             dim3 g(ngen, 1);
             if (odd) { DISPATCH_COLL(true, (launch_scalar<COLL, ODD>(h, pg, true, g))) } else { DISPATCH_COLL(false, (launch_scalar<COLL, ODD>(h, pg, true, g))) }
             h->launches++;
         }
+        if (forked) h->stream = main;
+        if (general) p.segmask = h->segmask;
+        if (odd) { DISPATCH_COLL(true, (launch_vec<COLL, ODD>(h, p))) } else { DISPATCH_COLL(false, (launch_vec<COLL, ODD>(h, p))) }
+        h->launches++;
+        if (forked) { rc = join_side(h, main); if (rc) return rc; }
     }
     if (lagged) {
         reduce_partials(h, nparts);
@@ -840,6 +909,7 @@ extern "C" int lbm_adapter_prepass(lbm_handle* h) {
     if (h->cfg.collision != LBM_CM_OPTIMAL) return LBM_OK;
     CU(cudaSetDevice(h->cfg.device));
     { int rc0 = prepare_resources(h, false); if (rc0) return rc0; }
+    if (h->direct() && h->ibm_count) { int rc0 = check_ibm_coverage(h); if (rc0) return rc0; }
     if (h->direct()) {      // the pre-pass already reads the neighbours' edge rows
         wait_neighbours_kernel<<<1, 1, 0, h->stream>>>(h->sync_flags, h->peer[0].attached, h->peer[1].attached, (unsigned long long)h->timestep, h->sync_timeout);
         h->launches++;
@@ -854,7 +924,6 @@ extern "C" int lbm_adapter_prepass(lbm_handle* h) {
 // process sits in cudaMalloc would dead-lock until the handshake timeout.
 static int prepare_resources(lbm_handle* h, bool want_macros) {
     int rc;
-    if (h->direct() && h->ibm_count) { rc = check_ibm_coverage(h); if (rc) return rc; }
     if (use_vec(h) && is_general(h)) { rc = ensure_segments(h); if (rc) return rc; }
     if (want_macros) { rc = ensure_macros(h); if (rc) return rc; }
     if (h->cfg.collision == LBM_CM_OPTIMAL) {
@@ -877,6 +946,7 @@ static int run_steps(lbm_handle* h, int n, bool macros_last) {
     if (h->cfg.world > 1 && n > 1 && h->cfg.collision == LBM_CM_OPTIMAL) return fail(LBM_ERR_INVALID, "OptimalAdapter on several slabs needs the all-reduce of the grid sums between steps: nsteps must be 1");
     CU(cudaSetDevice(h->cfg.device));
     if (n > 0) { int rc = prepare_resources(h, macros_last); if (rc) return rc; }
+    if (n > 0 && direct && h->ibm_count) { int rc = check_ibm_coverage(h); if (rc) return rc; }
     for (int i = 0; i < n; i++) {
         if (handshake) {
             // every step touches cells the neighbours wrote (odd: their edge rows, even: what they stored into mine):
@@ -905,7 +975,8 @@ extern "C" int lbm_sync(lbm_handle* h) {
     if (h->direct()) {
         int to = 0;
         CU(cudaMemcpy(&to, h->sync_timeout, sizeof(int), cudaMemcpyDeviceToHost));
-        if (to) return fail(LBM_ERR_STATE, "a neighbour slab did not reach the previous time step within 10 s (peer-mapped handshake timed out); results are invalid");
+        if (to) return fail(LBM_ERR_STATE, std::string(to == 2 ? "a neighbour slab did not post its IBM node states" : "a neighbour slab did not reach the previous time step") +
+                            " within 10 s (peer-mapped handshake timed out at step " + std::to_string(h->timestep) + " of slab " + std::to_string(h->cfg.rank) + "); results are invalid");
     }
     return LBM_OK;
 }

@@ -625,7 +625,7 @@ __global__ void __launch_bounds__(1024) ibm_solve_kernel(const Params p, const I
     if ((d.need[0] || d.need[1]) && threadIdx.x == 0) {
         const long long t0 = clock64();
         while ((d.need[0] && d.my_flags[0] < t) || (d.need[1] && d.my_flags[1] < t)) {
-            if (clock64() - t0 > 20000000000ll) { *d.timed_out = 1; break; }
+            if (clock64() - t0 > 20000000000ll) { *d.timed_out = 2; break; }
             __nanosleep(200);
         }
         __threadfence_system();
