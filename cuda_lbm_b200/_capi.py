@@ -12,7 +12,8 @@ LIB_PATH = os.path.join(_HERE, "liblbm_b200.so")
 LBM_OK, LBM_ERR_INVALID, LBM_ERR_CUDA, LBM_ERR_STATE = 0, -1, -2, -3
 BGK, MRT, CM, CM_OPTIMAL = 0, 1, 2, 3
 QK_D1_STALE_F0, QK_D2_MRT_ROWS, QK_D3_ZOUHE_RHO, QK_D7_IBM_CLIP, QK_D8_IBM_2X2, QK_D11_BB_RAW = 1, 2, 4, 8, 16, 32
-QK_REFERENCE, QK_FIXED = 63, 0
+QK_D9_IBM_ZERO_TARGET = 64
+QK_REFERENCE, QK_FIXED = 127, 0
 ADAPTER_EXACT, ADAPTER_LAGGED = 0, 1
 PEER_DESC_BYTES = 128
 FLUID, BOUNCE_BACK, ZOU_HE_TOP, ZOU_HE_LEFT = 0, 1, 2, 3
@@ -30,7 +31,7 @@ SYMBOLS = [
     "lbm_host_alloc", "lbm_host_free",
     "lbm_velocity_error_sums", "lbm_taylor_green_error_sums", "lbm_row_mean_velocity",
     "lbm_checkpoint_bytes", "lbm_checkpoint_write", "lbm_checkpoint_read",
-    "lbm_ibm_exchange_floats", "lbm_ibm_pack", "lbm_ibm_unpack",
+    "lbm_ibm_exchange_floats", "lbm_ibm_pack", "lbm_ibm_unpack", "lbm_set_body_velocities", "lbm_move_body",
     "lbm_last_error",
 ]
 
@@ -116,6 +117,8 @@ def lib():
         "lbm_ibm_exchange_floats": [vp, C.POINTER(C.c_int64)],
         "lbm_ibm_pack": [vp, vp],
         "lbm_ibm_unpack": [vp, vp],
+        "lbm_set_body_velocities": [vp, C.c_int32, fp],
+        "lbm_move_body": [vp, C.c_int32, fp],
     }
     for name, args in sig.items():
         fn = getattr(L, name)

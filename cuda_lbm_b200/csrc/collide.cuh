@@ -20,7 +20,7 @@ namespace lbm {
 constexpr int Q = 9;
 
 // quirk bits (include/lbm_b200.h)
-constexpr int QK_D1 = 1, QK_D2 = 2, QK_D3 = 4, QK_D7 = 8, QK_D8 = 16, QK_D11 = 32;
+constexpr int QK_D1 = 1, QK_D2 = 2, QK_D3 = 4, QK_D7 = 8, QK_D8 = 16, QK_D11 = 32, QK_D9 = 64;
 
 // lattice tables — reference src/core/lbm_constants.cuh:13-31 (h_C, h_OPP, h_weights)
 __host__ __device__ __forceinline__ constexpr int cx(int q) { return (q == 1 || q == 5 || q == 8) ? 1 : ((q == 3 || q == 6 || q == 7) ? -1 : 0); }

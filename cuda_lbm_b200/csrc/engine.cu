@@ -56,6 +56,8 @@ struct lbm_handle {
     long long* nbr_nodes = nullptr; long long* nbr_src = nullptr; float* nbr_g = nullptr; int nbr_count = 0;
     // IBM
     std::vector<float> h_pts;
+    std::vector<float> h_vel; bool has_vel = false;        // IBMBody::velocities, parallel to h_pts (lbm_set_body_velocities)
+    float2* d_utarget = nullptr;
     float* d_pts = nullptr; long long* ibm_nodes = nullptr; int* sten_idx = nullptr; float* sten_w = nullptr;
     int* csr_row = nullptr; int* csr_k = nullptr; float* csr_w = nullptr;
     float* ibm_rho = nullptr; float2* ibm_uprev = nullptr; float2* ibm_lagF = nullptr; float2* ibm_force = nullptr;
@@ -181,7 +183,7 @@ extern "C" int lbm_destroy(lbm_handle* h) {
     for (int sd = 0; sd < 2; sd++)
         if (h->peer[sd].ipc_base && !(sd == 1 && h->peer[0].ipc_base == h->peer[1].ipc_base)) cudaIpcCloseMemHandle(h->peer[sd].ipc_base);
     void* ptrs[] = {h->sync_timeout, h->pop, h->flags, h->force_plane, h->ring, h->nbr_nodes, h->nbr_src, h->nbr_g, h->d_pts, h->ibm_nodes,
-                    h->sten_idx, h->sten_w, h->csr_row, h->csr_k, h->csr_w, h->ibm_rho, h->ibm_uprev, h->ibm_lagF, h->ibm_force, h->ibm_mail_idx,
+                    h->sten_idx, h->sten_w, h->csr_row, h->csr_k, h->csr_w, h->ibm_rho, h->ibm_uprev, h->ibm_lagF, h->ibm_force, h->ibm_mail_idx, h->d_utarget,
                     h->partials, h->stage, h->sums, h->avg, h->rho_out, h->u_out, h->mass_acc, h->segmask, h->gen_list, h->val_stage};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -377,7 +379,7 @@ struct gather_idx { const int* idx; const int* ord; int* out; __device__ void op
 // Bodies whose stencils share a lattice node are coupled through the spreading sum and form one group; a slab works on
 // every group it owns a node of, with ALL markers of the group, so that each slab of a group computes the same bits.
 // The stencil node ids follow ibm_stencil_kernel exactly (same float arithmetic).
-static void select_bodies(lbm_handle* h, std::vector<float>& act_pts, std::vector<long long>& all_nodes) {
+static void select_bodies(lbm_handle* h, std::vector<float>& act_pts, std::vector<float>& act_vel, std::vector<long long>& all_nodes) {
     const bool two = (h->cfg.quirks & LBM_QK_D8_IBM_2X2) != 0;
     const int w = two ? 2 : 4, lo = two ? 0 : -1, ss = w * w, nx = h->cfg.nx, ny = h->cfg.ny;
     const int np = (int)(h->h_pts.size() / 2), nb = (int)h->body_start.size();
@@ -414,9 +416,12 @@ static void select_bodies(lbm_handle* h, std::vector<float>& act_pts, std::vecto
         const int y = (int)(all_nodes[i] / nx);
         if (y >= h->y0 && y < h->y0 + h->nyl) owns[find(first_body[i])] = 1;
     }
-    act_pts.clear();
+    act_pts.clear(); act_vel.clear();
     for (int b = 0; b < nb; b++)
-        if (owns[find(b)]) act_pts.insert(act_pts.end(), h->h_pts.begin() + 2 * (size_t)h->body_start[b], h->h_pts.begin() + 2 * (size_t)body_end(b));
+        if (owns[find(b)]) {
+            act_pts.insert(act_pts.end(), h->h_pts.begin() + 2 * (size_t)h->body_start[b], h->h_pts.begin() + 2 * (size_t)body_end(b));
+            act_vel.insert(act_vel.end(), h->h_vel.begin() + 2 * (size_t)h->body_start[b], h->h_vel.begin() + 2 * (size_t)body_end(b));
+        }
 }
 
 static int rebuild_ibm(lbm_handle* h) {
@@ -427,28 +432,33 @@ static int rebuild_ibm(lbm_handle* h) {
         mark_ibm_kernel<<<(h->ibm_count + 255) / 256, 256, 0, h->stream>>>(h->flags, h->ibm_nodes, h->ibm_count, (long long)h->y0 * h->cfg.nx, h->nloc, 0);
         h->launches++;
     }
-    void* old[] = {h->d_pts, h->ibm_nodes, h->sten_idx, h->sten_w, h->csr_row, h->csr_k, h->csr_w, h->ibm_rho, h->ibm_uprev, h->ibm_lagF, h->ibm_force, h->ibm_mail_idx};
+    void* old[] = {h->d_pts, h->ibm_nodes, h->sten_idx, h->sten_w, h->csr_row, h->csr_k, h->csr_w, h->ibm_rho, h->ibm_uprev, h->ibm_lagF, h->ibm_force, h->ibm_mail_idx, h->d_utarget};
     CU(cudaStreamSynchronize(h->stream));
     for (void* p : old) if (p) cudaFree(p);
     h->d_pts = nullptr; h->ibm_nodes = nullptr; h->sten_idx = nullptr; h->sten_w = nullptr; h->csr_row = nullptr; h->csr_k = nullptr; h->csr_w = nullptr;
-    h->ibm_rho = nullptr; h->ibm_uprev = nullptr; h->ibm_lagF = nullptr; h->ibm_force = nullptr; h->ibm_mail_idx = nullptr;
+    h->ibm_rho = nullptr; h->ibm_uprev = nullptr; h->ibm_lagF = nullptr; h->ibm_force = nullptr; h->ibm_mail_idx = nullptr; h->d_utarget = nullptr;
     h->np_total = (int)(h->h_pts.size() / 2);
     h->np = 0; h->ibm_count = 0; h->nall = 0; h->ibm_rows.clear(); h->pre_for_ts = -1; h->ibm_mail_for_ts = -1;
     if (h->np_total == 0) return LBM_OK;
     // the markers this slab works on: all of them on a single slab, the bodies it owns a node of otherwise
-    std::vector<float> act_pts;
+    std::vector<float> act_pts, act_vel;
     std::vector<long long> all_nodes;
     const bool multi = h->cfg.world > 1;
     if (multi) {
-        select_bodies(h, act_pts, all_nodes);
+        select_bodies(h, act_pts, act_vel, all_nodes);
         h->nall = (long long)all_nodes.size();
         if (h->nall > h->mail_nodes)
             return fail(LBM_ERR_INVALID, "the bodies touch " + std::to_string(h->nall) + " lattice nodes, more than the IBM mailbox holds (lbm_config.ibm_mailbox_nodes = " + std::to_string(h->mail_nodes) + ")");
     }
     const std::vector<float>& pts = multi ? act_pts : h->h_pts;
+    const std::vector<float>& vel = multi ? act_vel : h->h_vel;
     h->np = (int)(pts.size() / 2);
     if (h->np == 0) return LBM_OK;
     const int np = h->np;
+    if (h->has_vel && !(h->cfg.quirks & LBM_QK_D9_IBM_ZERO_TARGET)) {
+        CU(dmalloc(h, &h->d_utarget, (size_t)np));
+        CU(cudaMemcpyAsync(h->d_utarget, vel.data(), (size_t)2 * np * 4, cudaMemcpyHostToDevice, h->stream));
+    }
     const bool two = (h->cfg.quirks & LBM_QK_D8_IBM_2X2) != 0;
     const int w = two ? 2 : 4, lo = two ? 0 : -1, ss = w * w;
     h->ibm_ss = ss;
@@ -524,13 +534,48 @@ extern "C" int lbm_add_body(lbm_handle* h, const float* pts, int32_t n) {
     if (n == 0) return LBM_OK;
     h->body_start.push_back((int)(h->h_pts.size() / 2));
     h->h_pts.insert(h->h_pts.end(), pts, pts + (size_t)2 * n);
+    h->h_vel.resize(h->h_pts.size(), 0.0f);
     int rc = rebuild_ibm(h);
     if (rc != LBM_OK) {         // leave the handle as it was before the call
         h->h_pts.resize((size_t)2 * h->body_start.back());
+        h->h_vel.resize(h->h_pts.size());
         h->body_start.pop_back();
         const std::string keep = g_err;
         rebuild_ibm(h);
         g_err = keep;
+    }
+    return rc;
+}
+
+static int body_range(lbm_handle* h, int body, size_t& first, size_t& count) {
+    if (!h) return fail(LBM_ERR_INVALID, "NULL handle");
+    const int nb = (int)h->body_start.size();
+    if (body < 0 || body >= nb) return fail(LBM_ERR_INVALID, "no such body");
+    first = (size_t)h->body_start[body];
+    count = (body + 1 < nb ? (size_t)h->body_start[body + 1] : h->h_pts.size() / 2) - first;
+    return LBM_OK;
+}
+
+extern "C" int lbm_set_body_velocities(lbm_handle* h, int32_t body, const float* vel) {
+    size_t first, count;
+    int rc = body_range(h, body, first, count); if (rc) return rc;
+    if (vel) { std::copy(vel, vel + 2 * count, h->h_vel.begin() + 2 * first); h->has_vel = true; }
+    else std::fill(h->h_vel.begin() + 2 * first, h->h_vel.begin() + 2 * (first + count), 0.0f);
+    return rebuild_ibm(h);
+}
+
+extern "C" int lbm_move_body(lbm_handle* h, int32_t body, const float* pts) {
+    size_t first, count;
+    int rc = body_range(h, body, first, count); if (rc) return rc;
+    if (!pts) return fail(LBM_ERR_INVALID, "NULL argument");
+    const std::vector<float> keep(h->h_pts.begin() + 2 * first, h->h_pts.begin() + 2 * (first + count));
+    std::copy(pts, pts + 2 * count, h->h_pts.begin() + 2 * first);
+    rc = rebuild_ibm(h);
+    if (rc != LBM_OK) {         // e.g. the moved body no longer fits the mailbox: back to where it was
+        std::copy(keep.begin(), keep.end(), h->h_pts.begin() + 2 * first);
+        const std::string msg = g_err;
+        rebuild_ibm(h);
+        g_err = msg;
     }
     return rc;
 }
@@ -699,6 +744,7 @@ static IbmData ibm_data(lbm_handle* h) {
     d.np = h->np; d.nnodes = h->ibm_count; d.ss = h->ibm_ss;
     d.nodes = h->ibm_nodes; d.sten_idx = h->sten_idx; d.sten_w = h->sten_w; d.row = h->csr_row; d.csr_k = h->csr_k; d.csr_w = h->csr_w;
     d.rho = h->ibm_rho; d.uprev = h->ibm_uprev; d.lagF = h->ibm_lagF; d.force = h->ibm_force;
+    d.utarget = h->d_utarget;
     d.mail_idx = h->ibm_mail_idx; d.mail = h->ibm_mail;
     d.my_flags = h->sync_flags + 2; d.timed_out = h->sync_timeout;
     for (int sd = 0; sd < 2; sd++) {

@@ -513,6 +513,7 @@ struct IbmData {
     const int* row;                     // CSR node -> (marker, weight), markers ascending
     const int* csr_k; const float* csr_w;
     float* rho; float2* uprev; float2* lagF; float2* force;     // scratch + result
+    const float2* utarget;              // [np] IBMBody::velocities, or nullptr = the reference's literal 0 (IBM_impl.cuh:15)
     // bodies across slab faces: the node states travel through a mailbox indexed by the GLOBAL stencil-node list
     // (IBM_MAIL floats per node), which every slab holds at the same offsets
     const int* mail_idx;                // [nnodes] mailbox slot of each node of this slab's (active) list
@@ -554,7 +555,8 @@ __device__ __forceinline__ void ibm_iterations(const Params& p, const IbmData& d
                 float2 u = d.uprev[idx];
                 rho += w * d.rho[idx]; ux += w * u.x; uy += w * u.y;
             }
-            float Fx = 2.0f * rho * (0.0f - ux), Fy = 2.0f * rho * (0.0f - uy);
+            const float2 ut = d.utarget ? d.utarget[k] : make_float2(0.0f, 0.0f);
+            float Fx = 2.0f * rho * (ut.x - ux), Fy = 2.0f * rho * (ut.y - uy);
             if (clip) { Fx = Fx > 1e-8f ? Fx : 0.0f; Fy = Fy > 1e-8f ? Fy : 0.0f; }
             d.lagF[k] = make_float2(Fx, Fy);
         }

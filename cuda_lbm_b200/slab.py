@@ -100,7 +100,7 @@ class SlabSolver:
         self.group = group
         self._sums = torch.zeros(3, dtype=torch.float64, device=device)
         self._device = device
-        self._ibm = None            # exchange buffer of the IBM node states, sized at the first step (bodies are added after construction)
+        self._ibm = None            # exchange buffer of the IBM node states (sized per step: bodies may be added or moved)
         self.collectives = 0
         self.mode = mode if self.world > 1 else "single"
         if self.mode == "direct":
@@ -121,10 +121,10 @@ class SlabSolver:
     def _exchange_ibm(self):
         """Bodies across slab faces, halo coupling: every slab contributes the states of the stencil nodes it owns (zeros
         elsewhere), so the sum over slabs is a gather — bit-exact, whatever order the all-reduce adds in."""
-        if self._ibm is None:
-            nf = getattr(self.e, "ibm_exchange_floats", lambda: 0)()
+        nf = getattr(self.e, "ibm_exchange_floats", lambda: 0)()      # changes when bodies are added or moved
+        if self._ibm is None or self._ibm.numel() != nf:
             self._ibm = torch.zeros(nf, dtype=torch.float32, device=self._device)
-        if self._ibm.numel() == 0:
+        if nf == 0:
             return
         self.e.ibm_pack(self._ibm.data_ptr())
         dist.all_reduce(self._ibm, group=self.group)

@@ -97,6 +97,17 @@ class Engine:
         p = np.ascontiguousarray(points, np.float32).reshape(-1)
         check(lib().lbm_add_body(self._h, _fp(p), p.size // 2))
 
+    def set_body_velocities(self, body, velocities):
+        if velocities is None:
+            check(lib().lbm_set_body_velocities(self._h, body, None))
+            return
+        v = np.ascontiguousarray(velocities, np.float32).reshape(-1)
+        check(lib().lbm_set_body_velocities(self._h, body, _fp(v)))
+
+    def move_body(self, body, points):
+        p = np.ascontiguousarray(points, np.float32).reshape(-1)
+        check(lib().lbm_move_body(self._h, body, _fp(p)))
+
     def init_fields(self, rho, u):
         rho = np.ascontiguousarray(rho, np.float32).reshape(-1)
         u = np.ascontiguousarray(u, np.float32).reshape(-1)

@@ -222,6 +222,9 @@ public:
         Scenario::add_bodies();
         for (const IBMBody& b : Scenario::IBM_bodies) {
             LBM_B200_CALL(lbm_add_body(h, b.points, b.num_points));
+            // IBMBody::velocities: dead data in the reference (IBM_impl.cuh:15, A-D9) and here under LBM_QK_D9_IBM_ZERO_TARGET
+            // (part of LBM_QK_REFERENCE); with that bit cleared (LBM_B200_QUIRKS) the markers force the fluid towards them
+            if (b.velocities && b.num_points > 0) LBM_B200_CALL(lbm_set_body_velocities(h, (int)bodies.size(), b.velocities));
             bodies.push_back(b);
         }
     }

@@ -44,7 +44,8 @@ extern "C" {
 #define LBM_QK_D7_IBM_CLIP 8   /* src/IBM/IBM_impl.cuh:20-24,41-44 — positive-only clipping */
 #define LBM_QK_D8_IBM_2X2 16   /* src/IBM/IBM_impl.cu:19-21,132-134 — 2x2 stencil */
 #define LBM_QK_D11_BB_RAW 32   /* src/functors/boundaryConditions/bbDomainBoundary.cuh:35-36 */
-#define LBM_QK_REFERENCE 63
+#define LBM_QK_D9_IBM_ZERO_TARGET 64 /* src/IBM/IBM_impl.cuh:15 — direct forcing targets u = 0; IBMBody::velocities are dead data */
+#define LBM_QK_REFERENCE 127
 #define LBM_QK_FIXED 0
 
 /* how CM<2,OptimalAdapter> obtains the grid means of rho, rho|u|, |Pi| (src/core/macroscopics/macroscopics.cuh:51-120,161-177) */
@@ -129,6 +130,13 @@ int lbm_set_body_force(lbm_handle* h, float fx, float fy);
  * bodies.  With several slabs EVERY slab is given EVERY body, in the same order: a slab works on the bodies whose
  * stencils reach into its rows (bodies that share lattice nodes count as one) and ignores the rest. */
 int lbm_add_body(lbm_handle* h, const float* points_aos, int32_t num_points);
+/* IBMBody::velocities (src/IBM/IBMBody.cuh:33-45), AoS [i*2+c], for body `body` (index in lbm_add_body order): the velocity its
+ * markers force the fluid towards.  The reference uploads them and then targets a literal 0 (src/IBM/IBM_impl.cuh:15, SURVEY
+ * A-D9), which LBM_QK_D9_IBM_ZERO_TARGET reproduces: they take effect only with that bit clear.  NULL = zero. */
+int lbm_set_body_velocities(lbm_handle* h, int32_t body, const float* velocities_aos);
+/* Move body `body`: new marker positions (same count as added).  The marker->node structure is rebuilt on the GPU
+ * (a few small kernels and sorts over O(markers); synchronises).  No reference counterpart (its bodies are static). */
+int lbm_move_body(lbm_handle* h, int32_t body, const float* points_aos);
 
 /* LBM<2>::init<Scenario>() — src/core/init/init.cuh:45-86: rho,u = the Init functor evaluated for every
  * node of the GLOBAL grid (host memory); populations are set to f_eq(rho,u), timestep = 0. */

@@ -37,7 +37,8 @@
 #define QK_D7_IBM_CLIP     8   /* IBM_impl.cuh:20-24,41-44  keep only values > 1e-8               */
 #define QK_D8_IBM_2X2      16  /* IBM_impl.cu:19-21,132-134  2x2 stencil under a 4-point delta    */
 #define QK_D11_BB_RAW      32  /* bbDomainBoundary.cuh:35-36  raw neighbour test ignores periodic */
-#define QK_ALL             63
+#define QK_D9_IBM_ZERO_TARGET 64 /* IBM_impl.cuh:15  target velocity hard-coded 0, IBMBody::velocities dead data */
+#define QK_ALL             127
 
 /* BC_flag — lbm_constants.cuh:377-397 */
 enum {
@@ -88,6 +89,7 @@ typedef struct {
     /* IBM  IBMManager.cuh:31-52 */
     int np;
     float *pts, *lag_u, *lag_rho, *lag_force, *u_prev, *f_iter;
+    float *lag_target;      /* IBMBody::velocities, AoS [i*2+c] (NULL = none given) */
 } oracle_t;
 
 /* ------------------------------------------------------------------ lifecycle */
@@ -112,7 +114,7 @@ void oracle_destroy(oracle_t *o) {
     if (!o) return;
     free(o->f); free(o->f_back); free(o->f_eq); free(o->rho); free(o->u); free(o->force);
     free(o->pi_mag); free(o->flags); free(o->bc_snapshot);
-    free(o->pts); free(o->lag_u); free(o->lag_rho); free(o->lag_force); free(o->u_prev); free(o->f_iter);
+    free(o->pts); free(o->lag_u); free(o->lag_rho); free(o->lag_force); free(o->u_prev); free(o->f_iter); free(o->lag_target);
     free(o);
 }
 
@@ -125,11 +127,21 @@ void oracle_set_omega(oracle_t *o, float tau, float omega) { o->tau = tau; o->om
 void oracle_set_markers(oracle_t *o, const float *pts_aos, int np) {
     size_t n = (size_t)o->nx * o->ny;
     free(o->pts); free(o->lag_u); free(o->lag_rho); free(o->lag_force); free(o->u_prev); free(o->f_iter);
+    free(o->lag_target); o->lag_target = NULL;
     o->np = np;
     o->pts = (float *)malloc(sizeof(float) * 2 * np);
     memcpy(o->pts, pts_aos, sizeof(float) * 2 * np);
     o->lag_u = (float *)calloc(2 * np, 4); o->lag_rho = (float *)calloc(np, 4); o->lag_force = (float *)calloc(2 * np, 4);
     o->u_prev = (float *)calloc(2 * n, 4); o->f_iter = (float *)calloc(2 * n, 4);
+}
+
+/* IBMBody::velocities (IBMBody.cuh:33-45).  The reference uploads them and then forces towards a literal 0
+ * (IBM_impl.cuh:15, Appendix A-D9): with QK_D9_IBM_ZERO_TARGET they are ignored, without it u_target = velocities. */
+void oracle_set_marker_velocities(oracle_t *o, const float *vel_aos) {
+    free(o->lag_target); o->lag_target = NULL;
+    if (!vel_aos || o->np == 0) return;
+    o->lag_target = (float *)malloc(sizeof(float) * 2 * o->np);
+    memcpy(o->lag_target, vel_aos, sizeof(float) * 2 * o->np);
 }
 
 /* ------------------------------------------------------------------ equilibrium */
@@ -514,7 +526,8 @@ static void ibm_multi_direct(oracle_t *o) {
         for (int k = 0; k < np; k++)
             for (int d = 0; d < 2; d++) {
                 float uu = o->lag_u[d * np + k];
-                float force = 2.0f * o->lag_rho[k] * (0.0f - uu);
+                float ut = (o->lag_target && !(o->quirks & QK_D9_IBM_ZERO_TARGET)) ? o->lag_target[2 * k + d] : 0.0f;   /* :15 u_target */
+                float force = 2.0f * o->lag_rho[k] * (ut - uu);
                 if (o->quirks & QK_D7_IBM_CLIP) force = force > 1e-8f ? force : 0.0f;
                 o->lag_force[d * np + k] = force;
             }

@@ -16,7 +16,8 @@ _LIB = None
 BGK, MRT, CM, CM_OPT = 0, 1, 2, 3
 # quirk bits, lbm_oracle.c
 QK_D1_STALE_F0, QK_D2_MRT_ROWS, QK_D3_ZOUHE_RHO, QK_D7_IBM_CLIP, QK_D8_IBM_2X2, QK_D11_BB_RAW = 1, 2, 4, 8, 16, 32
-QK_ALL = 63
+QK_D9_IBM_ZERO_TARGET = 64
+QK_ALL = 127
 # BC_flag  (reference src/core/lbm_constants.cuh:377-397)
 FLUID, BOUNCE_BACK, ZOU_HE_TOP, ZOU_HE_LEFT = 0, 1, 2, 3
 CYLINDER, ZG_OUTFLOW, PRESSURE_OUTLET, REGULARIZED_INLET_TOP = 6, 7, 8, 9
@@ -43,6 +44,7 @@ def lib():
         L.oracle_destroy.argtypes = [C.c_void_p]
         L.oracle_set_flags.argtypes = [C.c_void_p, ip]
         L.oracle_set_markers.argtypes = [C.c_void_p, fp, C.c_int]
+        L.oracle_set_marker_velocities.argtypes = [C.c_void_p, fp]
         L.oracle_init.argtypes = [C.c_void_p, fp, fp]
         L.oracle_set_populations.argtypes = [C.c_void_p, fp, fp]
         L.oracle_step.argtypes = [C.c_void_p, C.c_int]
@@ -103,6 +105,14 @@ class Oracle:
     def set_markers(self, pts):
         p = np.ascontiguousarray(pts, np.float32).reshape(-1)
         lib().oracle_set_markers(self._h, _fp(p), p.size // 2)
+
+    def set_marker_velocities(self, vel):
+        """IBMBody::velocities [np,2]; honoured only without QK_D9_IBM_ZERO_TARGET (quirks bit 64)."""
+        if vel is None:
+            lib().oracle_set_marker_velocities(self._h, None)
+            return
+        v = np.ascontiguousarray(vel, np.float32).reshape(-1)
+        lib().oracle_set_marker_velocities(self._h, _fp(v))
 
     def init(self, rho, u):
         rho = np.ascontiguousarray(rho, np.float32).reshape(-1)

@@ -130,3 +130,132 @@ def test_several_bodies_match_oracle(coll):
         dr = np.abs(e.macroscopics()[0] - o.macroscopics()[0]).max()
         assert df <= TOL_F * n ** 0.5 and dr <= TOL_RHO * n ** 0.5, (coll, n, df, dr)
     e.close()
+
+
+# ---------------------------------------------------------------- IBMBody::velocities and moving bodies (SURVEY A-D9, §8f-2)
+def _spin(points, centre, omega):
+    """rigid rotation about `centre`: the velocity of every marker"""
+    d = points - np.asarray(centre, np.float32)
+    return np.stack([-omega * d[:, 1], omega * d[:, 0]], axis=1).astype(np.float32)
+
+
+@pytest.mark.parametrize("quirks", [63, 0])
+def test_marker_velocities_match_oracle(quirks):
+    """With LBM_QK_D9_IBM_ZERO_TARGET clear the markers force the fluid towards IBMBody::velocities (a spinning cylinder);
+    engine and oracle agree to fp32 round-off, with the reference's other IBM defects on (63) and repaired (0)."""
+    body = _cyl(30.0, 24.0, 6.0, 40)
+    vel = _spin(body, (30.0, 24.0), 0.004)
+    case = _case("ibm_spin", cases.MRT, [body])
+    rho0, u0 = case.init_fields()
+    o, e = make_oracle(case, quirks), make_engine(case, quirks)
+    o.set_marker_velocities(vel); e.set_body_velocities(0, vel)
+    o.init(rho0, u0); e.init_fields(rho0, u0)
+    done = 0
+    for n in (1, 2, 3, 10, 40):
+        o.step(n - done); e.step(n - done, macroscopics=True); done = n
+        df = np.abs(e.populations() - o.populations()).max()
+        dr = np.abs(e.macroscopics()[0] - o.macroscopics()[0]).max()
+        assert df <= TOL_F * n ** 0.5 and dr <= TOL_RHO * n ** 0.5, (quirks, n, df, dr)
+    # the target velocities do something: the same run without them differs
+    e2 = make_engine(case, quirks)
+    e2.init_fields(rho0, u0)
+    e2.step(40)
+    assert np.abs(e2.populations() - e.populations()).max() > 1e-6
+    e.close(); e2.close()
+
+
+def test_marker_velocities_are_dead_data_with_the_reference_quirk():
+    """LBM_QK_REFERENCE (bit 64 set) reproduces the reference: velocities are carried and ignored (IBM_impl.cuh:15)."""
+    body = _cyl(30.0, 24.0, 6.0, 40)
+    case = _case("ibm_dead", cases.BGK, [body])
+    rho0, u0 = case.init_fields()
+    outs = []
+    for with_vel in (False, True):
+        e = make_engine(case, 127)
+        if with_vel:
+            e.set_body_velocities(0, _spin(body, (30.0, 24.0), 0.004))
+        e.init_fields(rho0, u0)
+        e.step(12)
+        outs.append(e.populations())
+        e.close()
+    assert np.array_equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("world", [1, 2])
+def test_moved_body_matches_oracle_and_slabs(world):
+    """lbm_move_body between steps (the body crosses the slab face while moving) against the oracle with re-set markers;
+    the two-slab run equals the single-handle run bit for bit."""
+    import torch
+    b0 = _cyl(30.0, 21.0, 4.0, 24)
+    other = _cyl(70.0, 30.0, 3.0, 12)
+    case = _case("ibm_move", cases.MRT, [b0, other])
+    rho0, u0 = case.init_fields()
+    shifts = [(0.0, 0.0), (0.37, 1.21), (0.74, 2.42), (1.11, 3.63)]
+    o = make_oracle(case)
+    o.init(rho0, u0)
+    engs = [make_engine(case, rank=r, world=world) for r in range(world)]
+    for e in engs:
+        e.init_fields(rho0, u0)
+    halo = {(r, s): torch.zeros(3 * case.nx, dtype=torch.float32, device="cuda") for r in range(world) for s in (0, 1)}
+
+    def step_all():
+        need = engs[0].next_step_needs_halo()
+        for phase in (("pre",) if need else ()):
+            _halo(phase)
+        nf = engs[0].ibm_exchange_floats()          # the moved body touches a different number of lattice nodes
+        assert all(e.ibm_exchange_floats() == nf for e in engs)
+        if nf:
+            bufs = [torch.zeros(nf, dtype=torch.float32, device="cuda") for _ in engs]
+            torch.cuda.synchronize()                # torch works on its own stream, the handles on theirs
+            for e, b in zip(engs, bufs):
+                e.ibm_pack(b.data_ptr())
+            for e in engs:
+                e.sync()
+            tot = torch.stack(bufs).sum(dim=0)
+            torch.cuda.synchronize()
+            for e in engs:
+                e.ibm_unpack(tot.data_ptr())
+        for e in engs:
+            e.step(1, macroscopics=True)
+        for e in engs:
+            e.sync()
+        if need:
+            _halo("post")
+
+    def _halo(phase):
+        # two slabs, non-periodic: slab 0's upper face (side 1) meets slab 1's lower face (side 0)
+        engs[0].halo("pack_" + phase, 1, halo[(0, 1)].data_ptr()); engs[1].halo("pack_" + phase, 0, halo[(1, 0)].data_ptr())
+        for e in engs:
+            e.sync()
+        engs[0].halo("unpack_" + phase, 1, halo[(1, 0)].data_ptr()); engs[1].halo("unpack_" + phase, 0, halo[(0, 1)].data_ptr())
+        for e in engs:
+            e.sync()
+
+    for (dx, dy) in shifts:
+        moved = (b0 + np.array([dx, dy], np.float32)).astype(np.float32)
+        o.set_markers(np.concatenate([moved, other], axis=0))
+        for e in engs:
+            e.move_body(0, moved)
+        for _ in range(4):
+            o.step(1)
+            step_all()
+    f = np.concatenate([e.populations() for e in engs], axis=0)
+    rho = np.concatenate([e.macroscopics()[0] for e in engs], axis=0)
+    for e in engs:
+        e.close()
+    n = 4 * len(shifts)
+    assert np.abs(f - o.populations()).max() <= TOL_F * n ** 0.5 and np.abs(rho - o.macroscopics()[0]).max() <= TOL_RHO * n ** 0.5
+    if world == 1:
+        test_moved_body_matches_oracle_and_slabs.single = f
+    elif getattr(test_moved_body_matches_oracle_and_slabs, "single", None) is not None:
+        assert np.array_equal(f, test_moved_body_matches_oracle_and_slabs.single)
+
+
+def test_body_index_is_checked():
+    import cuda_lbm_b200 as L
+    case = _case("ibm_idx", cases.BGK, ONE())
+    e = make_engine(case)
+    for call in (lambda: e.set_body_velocities(1, np.zeros((16, 2), np.float32)), lambda: e.move_body(-1, np.zeros((16, 2), np.float32))):
+        with pytest.raises(L.LbmError):
+            call()
+    e.close()

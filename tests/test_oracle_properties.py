@@ -101,3 +101,30 @@ def test_each_quirk_switch_changes_the_result(quirk, name):
         o.step(20)
         outs.append(o.populations())
     assert np.abs(outs[0] - outs[1]).max() > 1e-9
+
+
+def test_marker_velocities_dead_with_d9_and_drive_the_fluid_without():
+    """A-D9: the reference carries IBMBody::velocities and forces towards a literal 0 (IBM_impl.cuh:15).  With the quirk bit set
+    they change nothing; with it clear (and the clipping defect D7 repaired) the fluid inside a spinning ring picks up the spin."""
+    c = cases.Case("spin", 64, 64, cases.BGK, 1.0 / 6.0, (True, True), 0.04, "cyl_ibm")
+    c.flags = lambda: np.zeros((64, 64), np.int32)
+    ring = O.create_cylinder(32.0, 32.0, 10.0, 64)
+    d = ring - np.float32(32.0)
+    w = 0.002
+    vel = np.stack([-w * d[:, 1], w * d[:, 0]], axis=1).astype(np.float32)
+    c.bodies = [ring]
+    rho0, u0 = np.ones((64, 64), np.float32), np.zeros((64, 64, 2), np.float32)
+    outs = {}
+    for q, with_vel in ((O.QK_ALL, False), (O.QK_ALL, True), (0, True)):
+        o = cases.make_oracle(c, quirks=q)
+        if with_vel:
+            o.set_marker_velocities(vel)
+        o.init(rho0, u0)
+        o.step(300)
+        outs[(q, with_vel)] = o.macroscopics()[1]
+    assert np.array_equal(outs[(O.QK_ALL, False)], outs[(O.QK_ALL, True)])
+    u = outs[(0, True)]
+    y, x = np.meshgrid(np.arange(64) - 32.0, np.arange(64) - 32.0, indexing="ij")
+    near = np.abs(np.hypot(x, y) - 10.0) < 1.0
+    circ = (x * u[..., 1] - y * u[..., 0])[near].mean() / 10.0       # mean tangential velocity on the ring
+    assert 0.3 * w * 10 < circ < 1.2 * w * 10, circ

@@ -171,6 +171,7 @@ def _run_slabs(case, world, nsteps, adapter_mode=0, direct=False, chunk=1):
         for e in engs:
             e.sync()
         total = torch.stack(ibm_bufs).sum(dim=0)
+        torch.cuda.synchronize()                # torch works on its own stream, the handles on theirs
         for e in engs:
             e.ibm_unpack(total.data_ptr())
         for e in engs:
