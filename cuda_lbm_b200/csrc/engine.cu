@@ -48,6 +48,10 @@ struct lbm_handle {
     // the general-path work of a step (IBM pre-pass, boundary / body segments) runs beside the vectorised kernel on a second
     // stream: under the AA pattern a cell reads exactly the slots it overwrites, so the two kernels touch disjoint memory
     cudaStream_t side_stream = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr; bool overlap = true;
+    // small grids are bound by the host's launch rate, not by the GPU: lbm_step(h, n) replays a captured CUDA graph of
+    // 2*GRAPH_PAIRS steps (an odd/even pair repeats identically: only the parity of t reaches the kernels)
+    struct StepGraph { cudaGraphExec_t exec = nullptr; std::string key; long long launches = 0; int d_avg = 0, d_pre = 0, d_nbrg = 0; } graph[2];
+    int graph_mode = -1;            // LBM_B200_GRAPH: 0 never, 1 whenever possible, unset = slabs of up to 2^22 cells
     float* pop = nullptr;           // 9 (+1) planes
     int nplanes = 9;
     uint8_t* flags = nullptr;
@@ -187,6 +191,7 @@ extern "C" int lbm_destroy(lbm_handle* h) {
                     h->partials, h->stage, h->sums, h->avg, h->rho_out, h->u_out, h->mass_acc, h->segmask, h->gen_list, h->val_stage};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    for (auto& g : h->graph) if (g.exec) cudaGraphExecDestroy(g.exec);
     if (h->side_stream) cudaStreamDestroy(h->side_stream);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
@@ -234,6 +239,7 @@ extern "C" int lbm_create(const lbm_config* cfg, lbm_handle** out) {
             std::string m = cudaGetErrorString(cudaGetLastError()); lbm_destroy(h); return fail(LBM_ERR_CUDA, "stream / event creation failed: " + m);
         }
     }
+    if (const char* gm = getenv("LBM_B200_GRAPH")) h->graph_mode = gm[0] == '0' ? 0 : 1;
     h->perim = 2 * cfg->nx + 2 * cfg->ny;
     const size_t pop_floats = h->plane * h->nplanes;
     if (cfg->ibm_mailbox_nodes < 0) { cudaStreamDestroy(h->own_stream); delete h; return fail(LBM_ERR_INVALID, "ibm_mailbox_nodes < 0"); }
@@ -981,6 +987,79 @@ static int prepare_resources(lbm_handle* h, bool want_macros) {
     return LBM_OK;
 }
 
+// ------------------------------------------------------------------ CUDA-graph replay of step pairs (launch-bound grids)
+constexpr int GRAPH_PAIRS = 8;
+
+// everything a captured step bakes into its kernel arguments; a changed key re-captures
+static std::string graph_key(lbm_handle* h, int parity) {
+    std::string k;
+    auto add = [&k](const auto& v) { k.append(reinterpret_cast<const char*>(&v), sizeof(v)); };
+    const Params p = make_params(h, parity);
+    for (int q = 0; q < Q; q++) { add(p.A[q]); add(p.S[q]); }
+    add(p.A0[0]); add(p.A0[1]); add(p.nx); add(p.ny); add(p.y0); add(p.nyl); add(p.px); add(p.py); add(p.wrap_y); add(p.quirks); add(p.coll);
+    add(p.flags); add(p.omega); add(p.u_max); add(p.fx); add(p.fy); add(p.force_plane); add(p.ring); add(p.perim);
+    add(p.nbr_nodes); add(p.nbr_g); add(p.nbr_count); add(p.ibm_nodes); add(p.ibm_force); add(p.ibm_count); add(p.avg); add(p.nsx); add(p.plane);
+    const IbmData d = ibm_data(h);
+    add(d.np); add(d.ss); add(d.sten_idx); add(d.sten_w); add(d.row); add(d.csr_k); add(d.csr_w); add(d.rho); add(d.uprev); add(d.lagF); add(d.utarget);
+    add(h->nbr_src); add(h->segmask); add(h->gen_list); add(h->gen_count); add(h->partials); add(h->n_partials); add(h->stage); add(h->sums);
+    add(h->stream); add(h->side_stream); add(h->overlap); add(h->cfg.adapter_mode); add(parity);
+    return k;
+}
+
+static bool graph_eligible(const lbm_handle* h) {
+    if (h->cfg.world != 1 || h->stream == cudaStreamLegacy || h->stream == cudaStreamPerThread) return false;     // capture needs an ordinary stream
+    if (h->graph_mode >= 0) return h->graph_mode == 1;
+    return h->nloc <= (1ll << 22);
+}
+
+// captures 2*GRAPH_PAIRS steps starting at the current parity (nothing executes), leaves the host state untouched
+static int capture_steps(lbm_handle* h, lbm_handle::StepGraph& g, const std::string& key) {
+    if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+    const int ts = h->timestep, avg = h->avg_for_ts, pre = h->pre_for_ts, nbrg = h->nbrg_for_ts, mts = h->macros_ts;
+    const long long l0 = h->launches;
+    cudaStream_t main = h->stream;
+    CU(cudaStreamBeginCapture(main, cudaStreamCaptureModeThreadLocal));
+    int rc = LBM_OK;
+    for (int i = 0; i < 2 * GRAPH_PAIRS && rc == LBM_OK; i++) rc = one_step(h, false);
+    cudaGraph_t graph = nullptr;
+    h->stream = main;
+    cudaError_t e = cudaStreamEndCapture(main, &graph);
+    g.launches = h->launches - l0;
+    g.d_avg = h->avg_for_ts - h->timestep; g.d_pre = h->pre_for_ts - h->timestep; g.d_nbrg = h->nbrg_for_ts - h->timestep;
+    h->timestep = ts; h->avg_for_ts = avg; h->pre_for_ts = pre; h->nbrg_for_ts = nbrg; h->macros_ts = mts; h->launches = l0;
+    if (rc != LBM_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(LBM_ERR_CUDA, std::string("stream capture failed: ") + cudaGetErrorString(e)); }
+    e = cudaGraphInstantiate(&g.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) { g.exec = nullptr; cudaGetLastError(); return fail(LBM_ERR_CUDA, std::string("graph instantiation failed: ") + cudaGetErrorString(e)); }
+    g.key = key;
+    return LBM_OK;
+}
+
+// runs as many whole graphs as fit into n steps; returns the number of steps done
+static int run_graphs(lbm_handle* h, int n, int& done) {
+    done = 0;
+    if (n < 2 * GRAPH_PAIRS || !graph_eligible(h)) return LBM_OK;
+    const int parity = (h->timestep + 1) & 1;
+    // CM<2,OptimalAdapter>: the host decides per step whether the moments pre-pass runs (exact mode: unless the sums were handed
+    // in; lagged mode: only while no previous step has produced them).  A graph is captured, and replayed, in the steady state only.
+    if (h->cfg.collision == LBM_CM_OPTIMAL) {
+        const bool have = h->avg_for_ts == h->timestep + 1;
+        if (have != (h->cfg.adapter_mode == LBM_ADAPTER_LAGGED)) return LBM_OK;
+    }
+    lbm_handle::StepGraph& g = h->graph[parity];
+    const std::string key = graph_key(h, parity);
+    if (!g.exec || g.key != key) { int rc = capture_steps(h, g, key); if (rc) return rc; }
+    while (n - done >= 2 * GRAPH_PAIRS) {
+        CU(cudaGraphLaunch(g.exec, h->stream));
+        h->timestep += 2 * GRAPH_PAIRS;
+        h->launches += g.launches;
+        h->avg_for_ts = h->timestep + g.d_avg; h->pre_for_ts = h->timestep + g.d_pre; h->nbrg_for_ts = h->timestep + g.d_nbrg;
+        done += 2 * GRAPH_PAIRS;
+    }
+    return LBM_OK;
+}
+
 static int run_steps(lbm_handle* h, int n, bool macros_last) {
     if (!h) return fail(LBM_ERR_INVALID, "NULL handle");
     if (n < 0) return fail(LBM_ERR_INVALID, "nsteps < 0");
@@ -993,7 +1072,9 @@ static int run_steps(lbm_handle* h, int n, bool macros_last) {
     CU(cudaSetDevice(h->cfg.device));
     if (n > 0) { int rc = prepare_resources(h, macros_last); if (rc) return rc; }
     if (n > 0 && direct && h->ibm_count) { int rc = check_ibm_coverage(h); if (rc) return rc; }
-    for (int i = 0; i < n; i++) {
+    int first = 0;
+    if (!direct) { int rc = run_graphs(h, macros_last ? n - 1 : n, first); if (rc) return rc; }
+    for (int i = first; i < n; i++) {
         if (handshake) {
             // every step touches cells the neighbours wrote (odd: their edge rows, even: what they stored into mine):
             // wait until both have completed step t-1, and tell them when step t is done

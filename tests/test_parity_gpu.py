@@ -267,3 +267,35 @@ def test_peer_handshake_times_out_instead_of_hanging():
         engs[0].sync()
     for e in engs:
         e.close()
+
+
+# ---------------------------------------------------------------- CUDA-graph replay of step pairs (launch-bound grids)
+@pytest.mark.parametrize("name,adapter_mode", [("g_tg_bgk", 0), ("g_pois_mrt", 0), ("g_lid_cmopt", 0), ("g_lid_cmopt", 1), ("g_cyl_ibm_mrt", 0),
+                                               ("g_cyl_flag_bgk", 0), ("g_lid_cm", 0)])
+def test_graph_replay_is_bit_identical_to_stream_launches(name, adapter_mode, monkeypatch):
+    """lbm_step(h, n) replays captured graphs of 16 steps on small grids; the result must not depend on how n steps are cut
+    into graph replays and single launches, nor on whether graphs are used at all (LBM_B200_GRAPH=0)."""
+    case = cases.BY_NAME[name]
+    rho0, u0 = case.init_fields()
+
+    def run(chunks, graph):
+        monkeypatch.setenv("LBM_B200_GRAPH", graph)
+        e = make_engine(case, adapter_mode=adapter_mode)
+        e.init_fields(rho0, u0)
+        l0 = e.info().kernel_launches
+        for i, n in enumerate(chunks):
+            e.step(n, macroscopics=(i == len(chunks) - 1))
+        out = e.populations(), e.macroscopics(), e.info().timestep, e.info().kernel_launches - l0
+        e.close()
+        return out
+
+    steps = 53
+    f0, (r0, v0), t0, l_plain = run([steps], "0")
+    assert t0 == steps and np.isfinite(f0).all() or case.coll == cases.CM_OPT
+    for chunks in ([steps], [1, 16, 36], [17, 3, 33], [32, 21]):
+        f1, (r1, v1), t1, l_graph = run(chunks, "1")
+        assert t1 == steps and sum(chunks) == steps
+        assert np.array_equal(f0, f1, equal_nan=True), (name, chunks, np.nanmax(np.abs(f0 - f1)))
+        assert np.array_equal(r0, r1, equal_nan=True) and np.array_equal(v0, v1, equal_nan=True)
+        if chunks == [steps]:
+            assert l_graph == l_plain           # the launch counter counts the kernels inside the replayed graphs
