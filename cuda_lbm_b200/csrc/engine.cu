@@ -52,6 +52,7 @@ struct lbm_handle {
     // 2*GRAPH_PAIRS steps (an odd/even pair repeats identically: only the parity of t reaches the kernels)
     struct StepGraph { cudaGraphExec_t exec = nullptr; std::string key; long long launches = 0; int d_avg = 0, d_pre = 0, d_nbrg = 0; } graph[2];
     int graph_mode = -1;            // LBM_B200_GRAPH: 0 never, 1 whenever possible, unset = slabs of up to 2^22 cells
+    cudaEvent_t ev_bridge[2] = {nullptr, nullptr};      // legacy / per-thread user stream <-> own stream around graph replays
     float* pop = nullptr;           // 9 (+1) planes
     int nplanes = 9;
     uint8_t* flags = nullptr;
@@ -192,6 +193,7 @@ extern "C" int lbm_destroy(lbm_handle* h) {
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     for (auto& g : h->graph) if (g.exec) cudaGraphExecDestroy(g.exec);
+    for (auto& e : h->ev_bridge) if (e) cudaEventDestroy(e);
     if (h->side_stream) cudaStreamDestroy(h->side_stream);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
@@ -1007,7 +1009,7 @@ static std::string graph_key(lbm_handle* h, int parity) {
 }
 
 static bool graph_eligible(const lbm_handle* h) {
-    if (h->cfg.world != 1 || h->stream == cudaStreamLegacy || h->stream == cudaStreamPerThread) return false;     // capture needs an ordinary stream
+    if (h->cfg.world != 1) return false;
     if (h->graph_mode >= 0) return h->graph_mode == 1;
     return h->nloc <= (1ll << 22);
 }
@@ -1047,16 +1049,32 @@ static int run_graphs(lbm_handle* h, int n, int& done) {
         const bool have = h->avg_for_ts == h->timestep + 1;
         if (have != (h->cfg.adapter_mode == LBM_ADAPTER_LAGGED)) return LBM_OK;
     }
+    // the legacy default stream (the header shim works on it, as the reference does) and the per-thread stream cannot be captured:
+    // graphs are captured and replayed on the handle's own stream, ordered after / before the user's stream with two events
+    cudaStream_t user = h->stream;
+    const bool bridged = user == cudaStreamLegacy || user == cudaStreamPerThread;
+    if (bridged) {
+        for (auto& e : h->ev_bridge) if (!e) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        h->stream = h->own_stream;
+    }
     lbm_handle::StepGraph& g = h->graph[parity];
     const std::string key = graph_key(h, parity);
-    if (!g.exec || g.key != key) { int rc = capture_steps(h, g, key); if (rc) return rc; }
-    while (n - done >= 2 * GRAPH_PAIRS) {
-        CU(cudaGraphLaunch(g.exec, h->stream));
+    int rc = LBM_OK;
+    if (!g.exec || g.key != key) rc = capture_steps(h, g, key);
+    cudaError_t e = cudaSuccess;
+    if (rc == LBM_OK && bridged) { e = cudaEventRecord(h->ev_bridge[0], user); if (e == cudaSuccess) e = cudaStreamWaitEvent(h->stream, h->ev_bridge[0], 0); }
+    while (rc == LBM_OK && e == cudaSuccess && n - done >= 2 * GRAPH_PAIRS) {
+        e = cudaGraphLaunch(g.exec, h->stream);
+        if (e != cudaSuccess) break;
         h->timestep += 2 * GRAPH_PAIRS;
         h->launches += g.launches;
         h->avg_for_ts = h->timestep + g.d_avg; h->pre_for_ts = h->timestep + g.d_pre; h->nbrg_for_ts = h->timestep + g.d_nbrg;
         done += 2 * GRAPH_PAIRS;
     }
+    if (rc == LBM_OK && e == cudaSuccess && bridged) { e = cudaEventRecord(h->ev_bridge[1], h->stream); if (e == cudaSuccess) e = cudaStreamWaitEvent(user, h->ev_bridge[1], 0); }
+    h->stream = user;
+    if (rc != LBM_OK) return rc;
+    if (e != cudaSuccess) return fail(LBM_ERR_CUDA, std::string("graph replay failed: ") + cudaGetErrorString(e));
     return LBM_OK;
 }
 
