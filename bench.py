@@ -135,6 +135,8 @@ def main():
     ap.add_argument("--nx", type=int, default=NX)
     ap.add_argument("--ny", type=int, default=NY)
     ap.add_argument("--collision", default="BGK")
+    ap.add_argument("--rows-per-gpu", type=int, default=0,
+                    help="weak scaling: ny = rows-per-gpu * N (BASELINE configs[3]: 32768 x 4096*G slabs); default 0 = strong scaling on the fixed grid")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -159,6 +161,9 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     nx, ny = args.nx, args.ny
+    scaling = "strong"
+    if args.rows_per_gpu > 0:
+        ny, scaling = args.rows_per_gpu * world, "weak"
     coll = {"BGK": L.BGK, "MRT": L.MRT, "CM": L.CM, "CM_OPT": L.CM_OPTIMAL}[args.collision]
     scale = nx / 128.0
     eng = L.Engine(nx, ny, collision=coll, viscosity=NU, periodic=(True, True), u_max=0.04, device=local, rank=rank, world=world,
@@ -250,7 +255,7 @@ def main():
 
     if rank == 0:
         line = {"metric": "MLUPS", "value": mlups, "unit": "MLUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
                 "config": {"workload": f"taylor_green_d2q9_{args.collision.lower()}_{nx}x{ny}_periodic_yslab", "nx": nx, "ny": ny,
                            "collision": args.collision, "rows_per_gpu": eng.ny_local, "quirks": "reference-compatible", "slab_coupling": solver.mode,

@@ -143,6 +143,18 @@ def test_driver_protocol_equals_run(tmp_path):
         assert a[k] == b[k] == c[k], (k, a[k], b[k], c[k])
 
 
+def test_checkpoint_restart_through_the_driver(tmp_path):
+    """main --save-ckpt after 600 steps, then --load-ckpt + 400 steps in a new process: the same result line as 1000 steps in
+    one go (LBM::save_checkpoint / load_checkpoint<S> over lbm_checkpoint_write / lbm_checkpoint_read)."""
+    ck = str(tmp_path / "state.ckpt")
+    run_shim("ex_tg_mrt_256", tmp_path, "--steps", 600, "--save-int", 600, "--fast", "--save-ckpt", ck)
+    b, errors, out = run_shim("ex_tg_mrt_256", tmp_path, "--steps", 400, "--save-int", 400, "--fast", "--load-ckpt", ck)
+    a, _, _ = run_shim("ex_tg_mrt_256", tmp_path, "--steps", 1000, "--save-int", 1000, "--fast")
+    assert "restarted from" in out and "at step 600" in out
+    for k in ("error_pct", "mass_per_node", "mean_rho", "sum_u2"):
+        assert a[k] == b[k], (k, a[k], b[k])
+
+
 def test_poiseuille_profile(tmp_path):
     """64 x 32 channel, MRT, body force, wet-node bounce-back walls, to steady state (H^2/nu = 6.1e3 steps).
     The reference's metric assumes walls at y = 0 and y = NY (7.0 % predicted at NY = 32); against the
