@@ -32,6 +32,7 @@ SYMBOLS = [
     "lbm_velocity_error_sums", "lbm_taylor_green_error_sums", "lbm_row_mean_velocity",
     "lbm_checkpoint_bytes", "lbm_checkpoint_write", "lbm_checkpoint_read",
     "lbm_ibm_exchange_floats", "lbm_ibm_pack", "lbm_ibm_unpack", "lbm_set_body_velocities", "lbm_move_body",
+    "lbm_run_from_host",
     "lbm_last_error",
 ]
 
@@ -119,6 +120,7 @@ def lib():
         "lbm_ibm_unpack": [vp, vp],
         "lbm_set_body_velocities": [vp, C.c_int32, fp],
         "lbm_move_body": [vp, C.c_int32, fp],
+        "lbm_run_from_host": [vp, vp, vp, C.c_int32, vp, vp],
     }
     for name, args in sig.items():
         fn = getattr(L, name)

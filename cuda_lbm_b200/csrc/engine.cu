@@ -19,6 +19,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -53,7 +54,9 @@ struct lbm_handle {
     // 2*GRAPH_PAIRS steps (an odd/even pair repeats identically: only the parity of t reaches the kernels)
     struct StepGraph { cudaGraphExec_t exec = nullptr; std::string key; long long launches = 0; int d_avg = 0, d_pre = 0, d_nbrg = 0; } graph[2];
     int graph_mode = -1;            // LBM_B200_GRAPH: 0 never, 1 whenever possible, unset = slabs of up to 2^22 cells
-    cudaEvent_t ev_bridge[2] = {nullptr, nullptr};      // legacy / per-thread user stream <-> own stream around graph replays
+    cudaEvent_t ev_bridge[2] = {nullptr, nullptr};
+    // lbm_run_from_host: copy streams and per-band events of the time-skewed pipeline (engine_pipeline.inc)
+    cudaStream_t copy_in = nullptr, copy_out = nullptr; cudaEvent_t ev_pipe = nullptr; std::vector<cudaEvent_t> ev_band;      // legacy / per-thread user stream <-> own stream around graph replays
     float* pop = nullptr;           // 9 (+1) planes
     int nplanes = 9;
     uint8_t* flags = nullptr;
@@ -197,6 +200,10 @@ extern "C" int lbm_destroy(lbm_handle* h) {
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     for (auto& g : h->graph) if (g.exec) cudaGraphExecDestroy(g.exec);
     for (auto& e : h->ev_bridge) if (e) cudaEventDestroy(e);
+    for (auto& e : h->ev_band) cudaEventDestroy(e);
+    if (h->ev_pipe) cudaEventDestroy(h->ev_pipe);
+    if (h->copy_in) cudaStreamDestroy(h->copy_in);
+    if (h->copy_out) cudaStreamDestroy(h->copy_out);
     if (h->side_stream) cudaStreamDestroy(h->side_stream);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
@@ -370,9 +377,10 @@ extern "C" int lbm_set_force_field_device(lbm_handle* h, const float* d_force) {
 
 
 // The engine is ONE translation unit (every kernel template is instantiated once, every launch site sees the same
-// function pointers that lbm_create preloads); its host code is kept in four parts by subject:
+// function pointers that lbm_create preloads); its host code is kept in five parts by subject:
 #include "engine_ibm.inc"    // immersed bodies: structure build on the GPU, groups, mailbox slots
 #include "engine_step.inc"   // init, the time step, graph replay, read-back
+#include "engine_pipeline.inc" // lbm_run_from_host: a driver segment with the PCIe copies hidden behind the kernels
 #include "engine_io.inc"     // validation reductions, checkpoint / restart
 #include "engine_slab.inc"   // halo rows, peer-mapped neighbours
 

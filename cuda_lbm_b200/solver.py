@@ -142,6 +142,10 @@ class Engine:
         check(lib().lbm_get_macroscopics(self._h, rho.ctypes.data_as(C.c_void_p), u.ctypes.data_as(C.c_void_p)))
         return rho.reshape(self.ny_local, self.nx), u.reshape(self.ny_local, self.nx, 2)
 
+    def run_from_host(self, rho_ptr, u_ptr, nsteps, rho_out_ptr, u_out_ptr):
+        """One driver segment: host rho,u (this slab's rows) -> nsteps -> host rho,u; integer addresses of (ideally pinned) host memory."""
+        check(lib().lbm_run_from_host(self._h, C.c_void_p(rho_ptr), C.c_void_p(u_ptr), nsteps, C.c_void_p(rho_out_ptr), C.c_void_p(u_out_ptr)))
+
     def macroscopics_into(self, rho_ptr, u_ptr):
         """D2H into caller-owned (ideally pinned) host memory given as integer addresses."""
         check(lib().lbm_get_macroscopics(self._h, C.c_void_p(rho_ptr), C.c_void_p(u_ptr)))

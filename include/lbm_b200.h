@@ -166,6 +166,14 @@ int lbm_step(lbm_handle* h, int32_t nsteps);
  * +12 B/cell on that step only).  Required before lbm_get_macroscopics. */
 int lbm_step_with_macroscopics(lbm_handle* h, int32_t nsteps);
 
+/* One driver segment of the reference in one call (src/main.cu:77-147: init<Scenario>(), n iterations of the time loop,
+ * update_macroscopics()): populations from rho / u in host memory (this slab's rows, as lbm_init_fields_local), nsteps time
+ * steps, rho / u of the last step back into host memory (as lbm_get_macroscopics).  Same results, bit for bit, as those three
+ * calls.  When the slab is the whole periodic domain on the vectorised path, the slab is stepped in row bands in a time-skewed
+ * order so that the host->device copy, the kernels and the device->host copy of different bands overlap (pinned host memory,
+ * lbm_host_alloc, for full effect).  The output arrays may be the input arrays.  Blocks until the output is complete. */
+int lbm_run_from_host(lbm_handle* h, const float* rho_local, const float* u_aos_local, int32_t nsteps, float* rho_out_local, float* u_out_local);
+
 /* cudaDeviceSynchronize() of the reference's methods, once. */
 int lbm_sync(lbm_handle* h);
 

@@ -299,3 +299,52 @@ def test_graph_replay_is_bit_identical_to_stream_launches(name, adapter_mode, mo
         assert np.array_equal(r0, r1, equal_nan=True) and np.array_equal(v0, v1, equal_nan=True)
         if chunks == [steps]:
             assert l_graph == l_plain           # the launch counter counts the kernels inside the replayed graphs
+
+
+# ---------------------------------------------------------------- lbm_run_from_host: the time-skewed band pipeline
+@pytest.mark.parametrize("nx,ny,coll,nsteps", [(128, 200, cases.BGK, 1), (128, 200, cases.BGK, 2), (128, 200, cases.MRT, 5), (128, 200, cases.CM, 7),
+                                               (128, 200, cases.BGK, 30), (256, 1024, cases.BGK, 9), (64, 1000, cases.MRT, 40), (132, 64, cases.CM, 3)])
+def test_run_from_host_equals_the_three_calls(nx, ny, coll, nsteps):
+    """init from host fields + n steps + macroscopics to host in one call: row bands stepped in a time-skewed order while the other
+    bands are still being copied.  Same bits as lbm_init_fields + lbm_step_with_macroscopics + lbm_get_macroscopics, whether the
+    dependency wedges at the periodic seam stay apart (n small against the band count) or meet (n = 30 on 13 bands)."""
+    case = _tg_case(nx, ny, coll)
+    case.u_max = np.float32(0.04)
+    rho0, u0 = case.init_fields()
+    a = make_engine(case)
+    a.init_fields(rho0, u0)
+    a.step(nsteps, macroscopics=True)
+    r_a, u_a = a.macroscopics()
+    f_a = a.populations()
+    a.close()
+    b = make_engine(case)
+    rin, uin = np.ascontiguousarray(rho0, np.float32), np.ascontiguousarray(u0, np.float32)
+    rout, uout = np.full_like(rin, np.nan), np.full_like(uin, np.nan)
+    l0 = b.info().kernel_launches
+    b.run_from_host(rin.ctypes.data, uin.ctypes.data, nsteps, rout.ctypes.data, uout.ctypes.data)
+    assert b.info().timestep == nsteps and b.info().kernel_launches - l0 > nsteps       # many band launches, not n slab launches
+    f_b = b.populations()
+    r_b2, u_b2 = b.macroscopics()                   # the device copy of the result is valid as after lbm_step_with_macroscopics
+    b.step(3)                                       # and the handle carries on normally
+    b.sync()
+    b.close()
+    assert np.array_equal(rout, r_a) and np.array_equal(uout, u_a), (np.abs(rout - r_a).max(), np.abs(uout - u_a).max())
+    assert np.array_equal(f_b, f_a) and np.array_equal(r_b2, r_a) and np.array_equal(u_b2, u_a)
+
+
+def test_run_from_host_falls_back_where_the_pipeline_does_not_apply():
+    """Boundaries, bodies, OptimalAdapter: the same call runs the three steps one after the other — same results."""
+    for name in ("g_pois_mrt", "g_lid_cmopt", "g_cyl_ibm_mrt"):
+        case = cases.BY_NAME[name]
+        rho0, u0 = case.init_fields()
+        a = make_engine(case)
+        a.init_fields(rho0, u0)
+        a.step(6, macroscopics=True)
+        r_a, u_a = a.macroscopics()
+        a.close()
+        b = make_engine(case)
+        rin, uin = np.ascontiguousarray(rho0, np.float32), np.ascontiguousarray(u0, np.float32)
+        rout, uout = np.empty_like(rin), np.empty_like(uin)
+        b.run_from_host(rin.ctypes.data, uin.ctypes.data, 6, rout.ctypes.data, uout.ctypes.data)
+        b.close()
+        assert np.array_equal(rout, r_a, equal_nan=True) and np.array_equal(uout, u_a, equal_nan=True), name
