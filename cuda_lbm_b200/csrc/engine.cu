@@ -70,6 +70,7 @@ struct lbm_handle {
     float* d_pts = nullptr; long long* ibm_nodes = nullptr; int* sten_idx = nullptr; float* sten_w = nullptr;
     int* csr_row = nullptr; int* csr_k = nullptr; float* csr_w = nullptr;
     float* ibm_rho = nullptr; float2* ibm_uprev = nullptr; float2* ibm_lagF = nullptr; float2* ibm_force = nullptr;
+    int ibm_one_block_max = 8192;                // more markers / stencil nodes than this: seven many-block launches instead of one block (LBM_B200_IBM_ONE_BLOCK_MAX)
     int np = 0, ibm_count = 0, ibm_ss = 4;       // markers / stencil nodes this slab works on (world > 1: the bodies it owns a node of)
     // bodies across slab faces: every slab knows all bodies; node states travel through a mailbox indexed by the global node list
     std::vector<int> body_start;                 // first marker of each body in h_pts
@@ -164,7 +165,8 @@ static void preload_kernels(int device) {
     preload(moments_kernel<false>); preload(moments_kernel<true>); preload(moments_vec_kernel<false>); preload(moments_vec_kernel<true>);
     preload(reduce_stage1_kernel); preload(reduce_stage2_kernel); preload(sums_to_avg_kernel);
     preload(nbr_gather_kernel<false>); preload(nbr_gather_kernel<true>);
-    preload(ibm_kernel<false>); preload(ibm_kernel<true>); preload(ibm_gather_kernel<false>); preload(ibm_gather_kernel<true>); preload(ibm_solve_kernel);
+    preload(ibm_kernel<false>); preload(ibm_kernel<true>); preload(ibm_state_kernel<false>); preload(ibm_state_kernel<true>);
+    preload(ibm_markers_kernel); preload(ibm_nodes_kernel); preload(ibm_gather_kernel<false>); preload(ibm_gather_kernel<true>); preload(ibm_solve_kernel);
     preload(wait_neighbours_kernel); preload(signal_neighbours_kernel); preload(build_segmask_kernel);
     cudaGetLastError();
 }
@@ -252,6 +254,7 @@ extern "C" int lbm_create(const lbm_config* cfg, lbm_handle** out) {
         }
     }
     if (const char* gm = getenv("LBM_B200_GRAPH")) h->graph_mode = gm[0] == '0' ? 0 : 1;
+    if (const char* v = getenv("LBM_B200_IBM_ONE_BLOCK_MAX")) h->ibm_one_block_max = atoi(v);
     h->perim = 2 * cfg->nx + 2 * cfg->ny;
     const size_t pop_floats = h->plane * h->nplanes;
     if (cfg->ibm_mailbox_nodes < 0) { cudaStreamDestroy(h->own_stream); delete h; return fail(LBM_ERR_INVALID, "ibm_mailbox_nodes < 0"); }

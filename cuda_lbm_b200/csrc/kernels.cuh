@@ -542,38 +542,63 @@ __device__ __forceinline__ void ibm_node_state(const Params& p, long long node, 
     F = p.force_plane ? p.force_plane[ln] : make_float2(p.fx, p.fy);     // d_force after reset_forces, before accumulation
 }
 
+// One direct-forcing iteration in two halves, shared by the one-block kernels and the many-block kernels below.
+// Marker half: interpolate_velocities_kernel<2> (IBM_impl.cu:7-51) + compute_lagrangian_kernel (IBM_impl.cuh:9-26)
+__device__ __forceinline__ void ibm_marker_pass(const IbmData& d, int k, bool clip) {
+    float rho = 0.f, ux = 0.f, uy = 0.f;
+    for (int s = 0; s < d.ss; s++) {
+        int idx = d.sten_idx[k * d.ss + s];
+        if (idx < 0) continue;
+        float w = d.sten_w[k * d.ss + s];
+        float2 u = d.uprev[idx];
+        rho += w * d.rho[idx]; ux += w * u.x; uy += w * u.y;
+    }
+    const float2 ut = d.utarget ? d.utarget[k] : make_float2(0.0f, 0.0f);
+    float Fx = 2.0f * rho * (ut.x - ux), Fy = 2.0f * rho * (ut.y - uy);
+    if (clip) { Fx = Fx > 1e-8f ? Fx : 0.0f; Fy = Fy > 1e-8f ? Fy : 0.0f; }
+    d.lagF[k] = make_float2(Fx, Fy);
+}
+// Node half: spread_forces_kernel<2> (IBM_impl.cu:122-154, as a gather), correct_velocities_kernel + accumulate_forces_kernel (IBM_impl.cuh:30-68)
+__device__ __forceinline__ void ibm_node_pass(const IbmData& d, int i, bool clip) {
+    float fx = 0.f, fy = 0.f;
+    for (int e = d.row[i]; e < d.row[i + 1]; e++) { float2 F = d.lagF[d.csr_k[e]]; float w = d.csr_w[e]; fx += w * F.x; fy += w * F.y; }
+    float r2 = 2.0f * d.rho[i];
+    float2 u = d.uprev[i];
+    float cux = u.x + fx / r2, cuy = u.y + fy / r2;
+    if (clip) { cux = ((double)cux > 1e-8) ? cux : 0.0f; cuy = ((double)cuy > 1e-8) ? cuy : 0.0f; }
+    d.uprev[i] = make_float2(cux, cuy);
+    float2 F = d.force[i];
+    d.force[i] = make_float2(F.x + fx, F.y + fy);
+}
+
 // 3 iterations of interpolate -> Lagrangian force -> spread -> correct -> accumulate over d.rho / d.uprev / d.force (one block)
 __device__ __forceinline__ void ibm_iterations(const Params& p, const IbmData& d) {
     const bool clip = (p.quirks & QK_D7) != 0;
     for (int iter = 0; iter < 3; iter++) {                  // ITER_MAX (IBMManager.cuh:8)
-        for (int k = threadIdx.x; k < d.np; k += blockDim.x) {
-            float rho = 0.f, ux = 0.f, uy = 0.f;
-            for (int s = 0; s < d.ss; s++) {
-                int idx = d.sten_idx[k * d.ss + s];
-                if (idx < 0) continue;
-                float w = d.sten_w[k * d.ss + s];
-                float2 u = d.uprev[idx];
-                rho += w * d.rho[idx]; ux += w * u.x; uy += w * u.y;
-            }
-            const float2 ut = d.utarget ? d.utarget[k] : make_float2(0.0f, 0.0f);
-            float Fx = 2.0f * rho * (ut.x - ux), Fy = 2.0f * rho * (ut.y - uy);
-            if (clip) { Fx = Fx > 1e-8f ? Fx : 0.0f; Fy = Fy > 1e-8f ? Fy : 0.0f; }
-            d.lagF[k] = make_float2(Fx, Fy);
-        }
+        for (int k = threadIdx.x; k < d.np; k += blockDim.x) ibm_marker_pass(d, k, clip);
         __syncthreads();
-        for (int i = threadIdx.x; i < d.nnodes; i += blockDim.x) {
-            float fx = 0.f, fy = 0.f;
-            for (int e = d.row[i]; e < d.row[i + 1]; e++) { float2 F = d.lagF[d.csr_k[e]]; float w = d.csr_w[e]; fx += w * F.x; fy += w * F.y; }
-            float r2 = 2.0f * d.rho[i];
-            float2 u = d.uprev[i];
-            float cux = u.x + fx / r2, cuy = u.y + fy / r2;
-            if (clip) { cux = ((double)cux > 1e-8) ? cux : 0.0f; cuy = ((double)cuy > 1e-8) ? cuy : 0.0f; }
-            d.uprev[i] = make_float2(cux, cuy);
-            float2 F = d.force[i];
-            d.force[i] = make_float2(F.x + fx, F.y + fy);
-        }
+        for (int i = threadIdx.x; i < d.nnodes; i += blockDim.x) ibm_node_pass(d, i, clip);
         __syncthreads();
     }
+}
+
+// The same as seven launches of many blocks, for bodies too large for one block to be quick (tens of thousands of markers):
+// node states, then 3 x (marker half, node half).  Same per-marker / per-node arithmetic, hence the same bits.
+template <bool ODD>
+__global__ void __launch_bounds__(256) ibm_state_kernel(const Params p, const IbmData d) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d.nnodes) return;
+    float rho; float2 us, F;
+    ibm_node_state<ODD>(p, d.nodes[i], rho, us, F);
+    d.rho[i] = rho; d.uprev[i] = us; d.force[i] = F;
+}
+__global__ void __launch_bounds__(256) ibm_markers_kernel(const Params p, const IbmData d) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < d.np) ibm_marker_pass(d, k, (p.quirks & QK_D7) != 0);
+}
+__global__ void __launch_bounds__(256) ibm_nodes_kernel(const Params p, const IbmData d) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < d.nnodes) ibm_node_pass(d, i, (p.quirks & QK_D7) != 0);
 }
 
 // IBMManager<2>::multi_direct (src/IBM/IBMManager.cuh:222-252) as ONE launch working only on the nodes under

@@ -259,3 +259,24 @@ def test_body_index_is_checked():
         with pytest.raises(L.LbmError):
             call()
     e.close()
+
+
+@pytest.mark.parametrize("coll,nsteps", [(cases.MRT, 9), (cases.BGK, 40)])
+def test_many_block_ibm_path_is_bit_identical(coll, nsteps, monkeypatch):
+    """Bodies with more markers / stencil nodes than one block handles quickly (LBM_B200_IBM_ONE_BLOCK_MAX, default 8192) take seven
+    many-block launches per step instead of one block with barriers: same per-marker and per-node arithmetic, same bits —
+    also inside the replayed CUDA graphs (40 steps = two 16-step graphs + 8 launches)."""
+    case = _case("ibm_blocks", coll, THREE())
+    rho0, u0 = case.init_fields()
+    outs, launches = [], []
+    for limit in ("8192", "0"):
+        monkeypatch.setenv("LBM_B200_IBM_ONE_BLOCK_MAX", limit)
+        e = make_engine(case)
+        e.init_fields(rho0, u0)
+        l0 = e.info().kernel_launches
+        e.step(nsteps, macroscopics=True)
+        outs.append((e.populations(), e.macroscopics()))
+        launches.append(e.info().kernel_launches - l0)
+        e.close()
+    assert launches[1] == launches[0] + 6 * nsteps            # 7 launches instead of 1, every step
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1][1], outs[1][1][1])
