@@ -53,10 +53,24 @@ def test_no_cpu_fallback_argument_errors_without_gpu():
     assert L.lbm_create(C.byref(cfg), C.byref(h)) == _capi.LBM_ERR_INVALID
 
 
+def test_new_entry_points_follow_the_error_convention_without_gpu():
+    """Argument checks come before any device work: NULL handles / pointers return LBM_ERR_INVALID with a message, never crash."""
+    from cuda_lbm_b200 import _capi
+    L = _capi.lib()
+    two = (C.c_double * 2)()
+    n = C.c_int64()
+    for rc in (L.lbm_run_from_host(None, None, None, 1, None, None), L.lbm_checkpoint_write(None, b"/tmp/x"), L.lbm_checkpoint_read(None, None),
+               L.lbm_checkpoint_bytes(None, C.byref(n)), L.lbm_velocity_error_sums(None, None, two), L.lbm_taylor_green_error_sums(None, 0.1, 0.1, 0.0, two),
+               L.lbm_row_mean_velocity(None, None, None), L.lbm_ibm_exchange_floats(None, C.byref(n)), L.lbm_ibm_pack(None, None), L.lbm_ibm_unpack(None, None),
+               L.lbm_set_body_velocities(None, 0, None), L.lbm_move_body(None, 0, None)):
+        assert rc == _capi.LBM_ERR_INVALID
+        assert L.lbm_last_error()
+
+
 def test_product_package_never_imports_oracle():
     pkg = os.path.join(ROOT, "cuda_lbm_b200")
     for dp, _, fns in os.walk(pkg):
         for fn in fns:
-            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+            if fn.endswith((".py", ".cu", ".cuh", ".h", ".inc")):
                 txt = open(os.path.join(dp, fn)).read()
                 assert "oracle" not in txt.lower() or fn in (), f"{fn} mentions the oracle"
