@@ -13,8 +13,8 @@ A "step" is one time step of the whole grid = one launch of the fused kernel per
   value    MLUPS with the populations resident in HBM, timed with CUDA events on the launching stream, max over ranks
   e2e      the same K steps through the public API with HOST buffers inside the timed region: pinned host rho/u -> H2D ->
            K steps -> D2H of rho,u, i.e. one segment of the reference's driver loop (init once, update_macroscopics at the
-           save interval, src/main.cu:77-147).  N = 1: lbm_run_from_host (one call, copies and kernels pipelined over row
-           bands); N > 1: lbm_init_fields_local, the slab solver's steps, lbm_get_macroscopics
+           save interval, src/main.cu:77-147).  lbm_run_from_host per rank (one call, copies and kernels pipelined over
+           row bands; peer-mapped slabs synchronise their faces level by level on the device)
   roofline 72 B per cell-update (9 fp32 reads + 9 writes) / measured kernel time vs MEASURED_PEAKS.json
   cpu_baseline  the CPU oracle (oracle/lbm_oracle.c, OpenMP) on a bounded sample, rank 0, N = 1 only
 
@@ -234,16 +234,11 @@ def main():
         solver.barrier_after_init()
         barrier()
         t0 = time.perf_counter()
-        if world == 1:
-            # one call = one driver segment: H2D of the inputs, the steps and D2H of the result overlap band by band (lbm_run_from_host)
-            eng.run_from_host(h_rho.value, h_u.value, args.steps, h_rho.value, h_u.value)
-            api = "lbm_run_from_host (copies and kernels pipelined over row bands)"
-        else:
-            check(lib().lbm_init_fields_local(eng._h, h_rho, h_u))               # H2D of the segment's inputs (pinned host memory)
-            solver.barrier_after_init()
-            solver.step(args.steps, macroscopics=True)
-            eng.macroscopics_into(h_rho.value, h_u.value)                        # D2H of the result; blocks until done
-            api = "lbm_init_fields_local + lbm_step_with_macroscopics + lbm_get_macroscopics"
+        # one call per rank = one driver segment: H2D of the inputs, the steps and D2H of the result overlap band by band
+        # (lbm_run_from_host; peer-mapped slabs synchronise their faces level by level on the device)
+        solver.run_from_host(h_rho.value, h_u.value, args.steps, h_rho.value, h_u.value)
+        api = ("lbm_run_from_host (copies and kernels pipelined over row bands)" if solver.mode in ("single", "direct")
+               else "lbm_init_fields_local + lbm_step_with_macroscopics + lbm_get_macroscopics")
         barrier()
         dt = max_over_ranks(time.perf_counter() - t0)
         e2e = {"value": nx * ny * args.steps / dt / 1e6, "unit": "MLUPS",

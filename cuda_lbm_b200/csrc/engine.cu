@@ -56,7 +56,8 @@ struct lbm_handle {
     int graph_mode = -1;            // LBM_B200_GRAPH: 0 never, 1 whenever possible, unset = slabs of up to 2^22 cells
     cudaEvent_t ev_bridge[2] = {nullptr, nullptr};
     // lbm_run_from_host: copy streams and per-band events of the time-skewed pipeline (engine_pipeline.inc)
-    cudaStream_t copy_in = nullptr, copy_out = nullptr; cudaEvent_t ev_pipe = nullptr; std::vector<cudaEvent_t> ev_band;      // legacy / per-thread user stream <-> own stream around graph replays
+    cudaStream_t copy_in = nullptr, copy_out = nullptr; cudaEvent_t ev_pipe = nullptr; std::vector<cudaEvent_t> ev_band;
+    unsigned long long pipe_epoch = 0;           // number of pipelined calls on several slabs (tags the level counters)      // legacy / per-thread user stream <-> own stream around graph replays
     float* pop = nullptr;           // 9 (+1) planes
     int nplanes = 9;
     uint8_t* flags = nullptr;
@@ -168,6 +169,7 @@ static void preload_kernels(int device) {
     preload(ibm_kernel<false>); preload(ibm_kernel<true>); preload(ibm_state_kernel<false>); preload(ibm_state_kernel<true>);
     preload(ibm_markers_kernel); preload(ibm_nodes_kernel); preload(ibm_gather_kernel<false>); preload(ibm_gather_kernel<true>); preload(ibm_solve_kernel);
     preload(wait_neighbours_kernel); preload(signal_neighbours_kernel); preload(build_segmask_kernel);
+    preload(init_fields_kernel); preload(init_taylor_green_kernel);
     cudaGetLastError();
 }
 

@@ -131,6 +131,18 @@ class SlabSolver:
         self.e.ibm_unpack(self._ibm.data_ptr())
         self.collectives += 1
 
+    def run_from_host(self, rho_ptr, u_ptr, n, rho_out_ptr, u_out_ptr):
+        """One driver segment per rank: host rho,u of this slab -> n steps -> host rho,u (integer addresses, ideally pinned memory).
+        One slab, or peer-mapped slabs without OptimalAdapter: lbm_run_from_host (copies hidden behind the kernels, the slab faces
+        synchronised level by level on the device).  Otherwise the three calls with the barrier the handshake needs."""
+        if self.world == 1 or (self.mode == "direct" and not self.optimal):
+            self.e.run_from_host(rho_ptr, u_ptr, n, rho_out_ptr, u_out_ptr)
+            return
+        self.e.init_fields_local(rho_ptr, u_ptr)
+        self.barrier_after_init()
+        self.step(n, macroscopics=True)
+        self.e.macroscopics_into(rho_out_ptr, u_out_ptr)
+
     def step(self, n=1, macroscopics=False):
         if self.world == 1 or (self.mode == "direct" and not self.optimal):
             self.e.step(n, macroscopics=macroscopics)

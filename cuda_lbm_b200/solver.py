@@ -115,6 +115,13 @@ class Engine:
             raise ValueError("rho/u must cover the global grid")
         check(lib().lbm_init_fields(self._h, _fp(rho), _fp(u)))
 
+    def init_fields_local(self, rho_ptr, u_ptr):
+        """rho,u of this slab's rows from (ideally pinned) host memory given as integer addresses; asynchronous."""
+        check(lib().lbm_init_fields_local(self._h, C.c_void_p(rho_ptr), C.c_void_p(u_ptr)))
+
+    def reserve_macroscopics(self):
+        check(lib().lbm_reserve_macroscopics(self._h))
+
     def init_taylor_green(self, nu, u0):
         check(lib().lbm_init_taylor_green(self._h, float(np.float32(nu)), float(np.float32(u0))))
 

@@ -171,7 +171,10 @@ int lbm_step_with_macroscopics(lbm_handle* h, int32_t nsteps);
  * steps, rho / u of the last step back into host memory (as lbm_get_macroscopics).  Same results, bit for bit, as those three
  * calls.  When the slab is the whole periodic domain on the vectorised path, the slab is stepped in row bands in a time-skewed
  * order so that the host->device copy, the kernels and the device->host copy of different bands overlap (pinned host memory,
- * lbm_host_alloc, for full effect).  The output arrays may be the input arrays.  Blocks until the output is complete. */
+ * lbm_host_alloc, for full effect).  The output arrays may be the input arrays.  Blocks until the output is complete.
+ * Several slabs: supported with peer-mapped neighbours on both faces; every slab makes the call (one thread or process each), after
+ * all of them have finished their previous work (lbm_sync + barrier, as for lbm_init_*); the slab faces are synchronised level by
+ * level on the device. */
 int lbm_run_from_host(lbm_handle* h, const float* rho_local, const float* u_aos_local, int32_t nsteps, float* rho_out_local, float* u_out_local);
 
 /* cudaDeviceSynchronize() of the reference's methods, once. */

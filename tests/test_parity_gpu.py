@@ -348,3 +348,52 @@ def test_run_from_host_falls_back_where_the_pipeline_does_not_apply():
         b.run_from_host(rin.ctypes.data, uin.ctypes.data, 6, rout.ctypes.data, uout.ctypes.data)
         b.close()
         assert np.array_equal(rout, r_a, equal_nan=True) and np.array_equal(uout, u_a, equal_nan=True), name
+
+
+@pytest.mark.parametrize("nx,ny,world,coll,nsteps", [(128, 192, 3, cases.BGK, 5), (256, 1024, 2, cases.MRT, 9), (128, 512, 2, cases.CM, 40), (128, 256, 4, cases.BGK, 2)])
+def test_run_from_host_on_peer_mapped_slabs(nx, ny, world, coll, nsteps):
+    """lbm_run_from_host on several slabs: every slab pipelines its own bands and the deferred levels at the slab faces are
+    synchronised with the neighbours on the device.  One thread per slab (the call blocks); same bits as one handle."""
+    import threading
+    case = _tg_case(nx, ny, coll)
+    case.u_max = np.float32(0.04)
+    rho0, u0 = case.init_fields()
+    one = make_engine(case)
+    one.init_fields(rho0, u0)
+    one.step(nsteps, macroscopics=True)
+    r1, u1 = one.macroscopics()
+    one.step(3)
+    f1 = one.populations()
+    one.close()
+    engs = [make_engine(case, rank=r, world=world) for r in range(world)]
+    descs = [e.peer_export() for e in engs]
+    for r, e in enumerate(engs):
+        e.peer_attach(0, descs[(r - 1) % world]); e.peer_attach(1, descs[(r + 1) % world])
+        e.reserve_macroscopics()                    # no allocation while another slab's handshake kernel spins (one process here)
+    ins = [(np.ascontiguousarray(rho0[e.y0:e.y0 + e.ny_local]), np.ascontiguousarray(u0[e.y0:e.y0 + e.ny_local])) for e in engs]
+    outs = [(np.full_like(a, np.nan), np.full_like(b, np.nan)) for a, b in ins]
+    errs = []
+
+    def work(i):
+        try:
+            engs[i].run_from_host(ins[i][0].ctypes.data, ins[i][1].ctypes.data, nsteps, outs[i][0].ctypes.data, outs[i][1].ctypes.data)
+        except Exception as ex:          # noqa: BLE001
+            errs.append((i, ex))
+
+    ths = [threading.Thread(target=work, args=(i,)) for i in range(world)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join(120)
+    assert not errs, errs
+    rs, us = np.concatenate([o[0] for o in outs], axis=0), np.concatenate([o[1] for o in outs], axis=0)
+    assert np.array_equal(rs, r1) and np.array_equal(us, u1), (np.abs(rs - r1).max(), np.abs(us - u1).max())
+    # the ordinary per-step handshake carries on from step K
+    for e in engs:
+        e.step(3)
+    for e in engs:
+        e.sync()
+    fs = np.concatenate([e.populations() for e in engs], axis=0)
+    for e in engs:
+        e.close()
+    assert np.array_equal(fs, f1)
