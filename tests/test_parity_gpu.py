@@ -369,9 +369,13 @@ def test_run_from_host_on_peer_mapped_slabs(nx, ny, world, coll, nsteps):
     descs = [e.peer_export() for e in engs]
     for r, e in enumerate(engs):
         e.peer_attach(0, descs[(r - 1) % world]); e.peer_attach(1, descs[(r + 1) % world])
-        e.reserve_macroscopics()                    # no allocation while another slab's handshake kernel spins (one process here)
-    ins = [(np.ascontiguousarray(rho0[e.y0:e.y0 + e.ny_local]), np.ascontiguousarray(u0[e.y0:e.y0 + e.ny_local])) for e in engs]
-    outs = [(np.full_like(a, np.nan), np.full_like(b, np.nan)) for a, b in ins]
+    # pinned host memory, as a driver would use: nothing in the call then waits for the device while another slab's handshake
+    # kernel spins (the slabs share one process and one GPU here; pageable copies go through the driver's staging buffers)
+    import torch
+    ins = [(torch.from_numpy(np.ascontiguousarray(rho0[e.y0:e.y0 + e.ny_local])).pin_memory().numpy(),
+            torch.from_numpy(np.ascontiguousarray(u0[e.y0:e.y0 + e.ny_local])).pin_memory().numpy()) for e in engs]
+    outs = [(torch.full(a.shape, float("nan")).pin_memory().numpy(), torch.full(b.shape, float("nan")).pin_memory().numpy()) for a, b in ins]
+    torch.cuda.synchronize()
     errs = []
 
     def work(i):
