@@ -24,12 +24,14 @@ def _port():
         return s.getsockname()[1]
 
 
-@pytest.mark.parametrize("kind,mode,coll", [("tg", "direct", 0), ("tg", "nccl", 1), ("ibm", "direct", 1), ("ibm", "nccl", 1), ("ibm", "direct", 3), ("ibm", "nccl", 3)])
-def test_slabs_across_processes_match_single_gpu(kind, mode, coll):
+@pytest.mark.parametrize("kind,mode,coll,extra", [("tg", "direct", 0, ()), ("tg", "nccl", 1, ()), ("ibm", "direct", 1, ()), ("ibm", "nccl", 1, ()),
+                                                  ("ibm", "direct", 3, ()), ("ibm", "nccl", 3, ()), ("tg", "direct", 1, ("--from-host",)),
+                                                  ("tg", "nccl", 0, ("--from-host",))])
+def test_slabs_across_processes_match_single_gpu(kind, mode, coll, extra):
     n = min(_ngpu(), 4)
     if n < 2:
         pytest.skip("needs at least 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
-           "--master-port", str(_port()), os.path.join(HERE, "mp_slab_worker.py"), "--kind", kind, "--mode", mode, "--coll", str(coll)]
+           "--master-port", str(_port()), os.path.join(HERE, "mp_slab_worker.py"), "--kind", kind, "--mode", mode, "--coll", str(coll), *extra]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "MP_PARITY" in r.stdout and " OK" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])
