@@ -24,6 +24,7 @@ class FakeEngine:
     def __init__(self, rank, world, ibm_floats=0):
         self.rank, self.world, self.t = rank, world, 0
         self.ibm_floats, self.ibm_log = ibm_floats, []
+        self.calls = []
         self.log = []          # (step, phase, side, received tag)
         self.sums = np.array([1.0 + rank, 2.0, 3.0])
         self.set_sums = []
@@ -56,6 +57,17 @@ class FakeEngine:
     def adapter_prepass(self):
         pass
 
+    # driver segment from / to host memory (SlabSolver.run_from_host, halo coupling = the three calls with a barrier)
+    def init_fields_local(self, rho_ptr, u_ptr):
+        self.calls.append(("init", rho_ptr, u_ptr))
+        self.t = 0
+
+    def sync(self):
+        self.calls.append(("sync",))
+
+    def macroscopics_into(self, rho_ptr, u_ptr):
+        self.calls.append(("read", self.t, rho_ptr, u_ptr))
+
     # bodies across slab faces: slab r "owns" every world-th node state, the rest of its buffer is zero
     def ibm_exchange_floats(self):
         return self.ibm_floats
@@ -77,6 +89,13 @@ def _worker(rank, world, port, periodic, optimal, q, ibm_floats=0):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     e = FakeEngine(rank, world, ibm_floats)
     s = SlabSolver(e, NX, periodic, torch.device("cpu"), optimal_adapter=optimal, adapter_exact=True)
+    if ibm_floats == -1:            # the driver-segment call instead of plain stepping
+        e.ibm_floats = 0
+        s.run_from_host(11, 12, 4, 13, 14)
+        q.put((rank, e.log, e.calls, s.collectives))
+        dist.barrier()
+        dist.destroy_process_group()
+        return
     s.step(4)
     if ibm_floats:
         q.put((rank, e.ibm_log, None, s.collectives))
@@ -148,6 +167,15 @@ def test_ibm_node_states_are_gathered_by_allreduce_every_step(world):
             for r in range(world):
                 want[r::world] = 100 * (r + 1) + t
             assert np.array_equal(got, want), (rank, t, got, want)
+
+
+def test_run_from_host_with_the_halo_coupling_is_init_barrier_steps_readback():
+    """SlabSolver.run_from_host without peer-mapped neighbours: lbm_init_fields_local, sync + barrier, the stepped halo schedule
+    (2 odd steps of 4 -> a 'pre' and a 'post' message per face each), then the read-back of step 4 into the caller's buffers."""
+    res = _run(2, True, ibm_floats=-1)
+    for rank, (log, calls, _) in res.items():
+        assert calls[0] == ("init", 11, 12) and calls[1] == ("sync",) and calls[-1] == ("read", 4, 13, 14), calls
+        assert len(log) == 2 * 2 * 2
 
 
 def test_slab_rows_cover_the_grid():
