@@ -236,9 +236,24 @@ def main():
         t0 = time.perf_counter()
         # one call per rank = one driver segment: H2D of the inputs, the steps and D2H of the result overlap band by band
         # (lbm_run_from_host; peer-mapped slabs synchronise their faces level by level on the device)
-        solver.run_from_host(h_rho.value, h_u.value, args.steps, h_rho.value, h_u.value)
-        api = ("lbm_run_from_host (copies and kernels pipelined over row bands)" if solver.mode in ("single", "direct")
-               else "lbm_init_fields_local + lbm_step_with_macroscopics + lbm_get_macroscopics")
+        api, failed = None, 0.0
+        try:
+            solver.run_from_host(h_rho.value, h_u.value, args.steps, h_rho.value, h_u.value)
+            api = ("lbm_run_from_host (copies and kernels pipelined over row bands)" if solver.mode in ("single", "direct")
+                   else "lbm_init_fields_local + lbm_step_with_macroscopics + lbm_get_macroscopics")
+        except L.LbmError as ex:        # never lose the bench line over the e2e leg: every rank falls back together
+            failed, api = 1.0, f"fallback after: {ex}"
+        if max_over_ranks(failed) > 0:
+            eng.init_taylor_green(NU, 0.04 / scale)
+            eng.macroscopics_into(h_rho.value, h_u.value)
+            solver.barrier_after_init()
+            barrier()
+            t0 = time.perf_counter()
+            check(lib().lbm_init_fields_local(eng._h, h_rho, h_u))
+            solver.barrier_after_init()
+            solver.step(args.steps, macroscopics=True)
+            eng.macroscopics_into(h_rho.value, h_u.value)
+            api = "lbm_init_fields_local + lbm_step_with_macroscopics + lbm_get_macroscopics (" + (api or "another rank's lbm_run_from_host failed") + ")"
         barrier()
         dt = max_over_ranks(time.perf_counter() - t0)
         e2e = {"value": nx * ny * args.steps / dt / 1e6, "unit": "MLUPS",
