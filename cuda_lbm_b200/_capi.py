@@ -27,12 +27,12 @@ SYMBOLS = [
     "lbm_set_populations", "lbm_get_populations", "lbm_step", "lbm_step_with_macroscopics", "lbm_sync",
     "lbm_get_macroscopics", "lbm_get_macroscopics_device", "lbm_reserve_macroscopics", "lbm_total_mass", "lbm_moment_avg", "lbm_adapter_prepass",
     "lbm_set_moment_sums", "lbm_get_moment_sums", "lbm_info", "lbm_next_step_needs_halo", "lbm_halo_pack_pre",
-    "lbm_halo_unpack_pre", "lbm_halo_pack_post", "lbm_halo_unpack_post", "lbm_peer_export", "lbm_peer_attach", "lbm_peer_detach",
+    "lbm_halo_unpack_pre", "lbm_halo_pack_post", "lbm_halo_unpack_post", "lbm_peer_export", "lbm_peer_attach", "lbm_peer_attach_all", "lbm_peer_detach",
     "lbm_host_alloc", "lbm_host_free",
     "lbm_velocity_error_sums", "lbm_taylor_green_error_sums", "lbm_row_mean_velocity",
     "lbm_checkpoint_bytes", "lbm_checkpoint_write", "lbm_checkpoint_read",
     "lbm_ibm_exchange_floats", "lbm_ibm_pack", "lbm_ibm_unpack", "lbm_set_body_velocities", "lbm_move_body",
-    "lbm_run_from_host",
+    "lbm_run_from_host", "lbm_recover_macroscopics", "lbm_adapter_sums_pending",
     "lbm_last_error",
 ]
 
@@ -106,6 +106,7 @@ def lib():
         "lbm_halo_unpack_post": [vp, C.c_int, vp],
         "lbm_peer_export": [vp, vp],
         "lbm_peer_attach": [vp, C.c_int, vp],
+        "lbm_peer_attach_all": [vp, vp, C.c_int32],
         "lbm_peer_detach": [vp],
         "lbm_host_alloc": [C.POINTER(vp), C.c_int64],
         "lbm_host_free": [vp],
@@ -121,6 +122,8 @@ def lib():
         "lbm_set_body_velocities": [vp, C.c_int32, fp],
         "lbm_move_body": [vp, C.c_int32, fp],
         "lbm_run_from_host": [vp, vp, vp, C.c_int32, vp, vp],
+        "lbm_recover_macroscopics": [vp],
+        "lbm_adapter_sums_pending": [vp],
     }
     for name, args in sig.items():
         fn = getattr(L, name)

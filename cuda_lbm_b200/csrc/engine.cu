@@ -98,10 +98,15 @@ struct lbm_handle {
     // peer-mapped slab coupling (lbm_peer_export / lbm_peer_attach)
     unsigned long long* sync_flags = nullptr;      // 2 step counters written by the neighbours + padding, at the end of `pop`
     int* sync_timeout = nullptr;
-    struct Peer { float* base = nullptr; void* ipc_base = nullptr; long long plane = 0, off = 0; unsigned long long* flag = nullptr; bool attached = false;
-                  float* mail = nullptr; int y0 = 0, nyl = 0; } peer[2];
-    cudaIpcMemHandle_t peer_ipc[2]{};
+    struct Peer { float* base = nullptr; long long plane = 0, off = 0; unsigned long long* flag = nullptr; bool attached = false; int rank = -1; } peer[2];
     bool direct() const { return peer[0].attached || peer[1].attached; }
+    // every slab of the decomposition this handle has mapped (lbm_peer_attach_all maps all of them, lbm_peer_attach its neighbour):
+    // the device-side all-reduce of the adapter sums and the IBM node states of bodies across slab faces reach all of these
+    struct Mapped { char* base = nullptr; void* ipc_base = nullptr; long long flags_off = 0, mail_off = -1; int y0 = 0, nyl = 0; } mapped[MAX_WORLD];
+    SlabNet* d_net = nullptr;                      // device copy of the table the kernels use
+    bool all_mapped() const { for (int r = 0; r < cfg.world; r++) if (r != cfg.rank && !mapped[r].base) return false; return cfg.world > 1; }
+    int adp_published_ts = -1;                     // lagged OptimalAdapter on several slabs: sums for this step are on their way to every slab's mailbox
+    unsigned long long ibm_need_mask = 0;          // ranks that own stencil nodes of the bodies this slab works on
 };
 
 // what one slab tells its neighbours (lbm_peer_export); opaque to callers, LBM_PEER_DESC_BYTES long
@@ -111,10 +116,14 @@ struct PeerDesc {
     unsigned long long raw;         // device pointer, valid inside the exporting process
     long long plane;                // floats per slot plane
     long long flags_off;            // byte offset of the step / IBM stage counters inside the allocation
-    long long mail_off;             // byte offset of the IBM mailbox inside the allocation
+    long long mail_off;             // byte offset of the IBM mailbox inside the allocation (the IBM stage counters sit at flags_off + TAIL_STAGE_OFF,
+                                    // the adapter mailbox at flags_off + TAIL_ADP_OFF)
     int nx, nyl, device, rank, y0, mail_nodes;
 };
 static_assert(sizeof(PeerDesc) <= LBM_PEER_DESC_BYTES, "PeerDesc must fit the ABI buffer");
+// tail of the population allocation (reached by the other slabs through the same mapping): 32 step / stage / level counters,
+// the per-source-rank IBM stage counters, the adapter mailbox, then the IBM node mailbox
+constexpr size_t TAIL_STAGE_OFF = 256, TAIL_ADP_OFF = TAIL_STAGE_OFF + MAX_WORLD * 8, TAIL_FIXED_BYTES = TAIL_ADP_OFF + 2 * MAX_WORLD * sizeof(AdpSlot);
 
 template <typename T>
 static cudaError_t dmalloc(lbm_handle* h, T** p, size_t count) {
@@ -164,7 +173,8 @@ static void preload_kernels(int device) {
     done[device] = true;
     preload_coll<C_BGK>(); preload_coll<C_MRT>(); preload_coll<C_CM>(); preload_coll<C_CMOPT>();
     preload(moments_kernel<false>); preload(moments_kernel<true>); preload(moments_vec_kernel<false>); preload(moments_vec_kernel<true>);
-    preload(reduce_stage1_kernel); preload(reduce_stage2_kernel); preload(sums_to_avg_kernel);
+    preload(reduce_stage1_kernel); preload(reduce_stage2_kernel); preload(sums_to_avg_kernel); preload(adapter_collect_kernel);
+    preload(recover_macros_kernel<false>); preload(recover_macros_kernel<true>);
     preload(nbr_gather_kernel<false>); preload(nbr_gather_kernel<true>);
     preload(ibm_kernel<false>); preload(ibm_kernel<true>); preload(ibm_state_kernel<false>); preload(ibm_state_kernel<true>);
     preload(ibm_markers_kernel); preload(ibm_nodes_kernel); preload(ibm_gather_kernel<false>); preload(ibm_gather_kernel<true>); preload(ibm_solve_kernel);
@@ -195,9 +205,8 @@ extern "C" int lbm_destroy(lbm_handle* h) {
     if (!h) return LBM_OK;
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    for (int sd = 0; sd < 2; sd++)
-        if (h->peer[sd].ipc_base && !(sd == 1 && h->peer[0].ipc_base == h->peer[1].ipc_base)) cudaIpcCloseMemHandle(h->peer[sd].ipc_base);
-    void* ptrs[] = {h->sync_timeout, h->pop, h->flags, h->force_plane, h->ring, h->nbr_nodes, h->nbr_src, h->nbr_g, h->d_pts, h->ibm_nodes,
+    for (auto& m : h->mapped) if (m.ipc_base) cudaIpcCloseMemHandle(m.ipc_base);
+    void* ptrs[] = {h->d_net, h->sync_timeout, h->pop, h->flags, h->force_plane, h->ring, h->nbr_nodes, h->nbr_src, h->nbr_g, h->d_pts, h->ibm_nodes,
                     h->sten_idx, h->sten_w, h->csr_row, h->csr_k, h->csr_w, h->ibm_rho, h->ibm_uprev, h->ibm_lagF, h->ibm_force, h->ibm_mail_idx, h->d_utarget,
                     h->partials, h->stage, h->sums, h->avg, h->rho_out, h->u_out, h->mass_acc, h->segmask, h->gen_list, h->val_stage};
     for (void* p : ptrs) if (p) cudaFree(p);
@@ -221,6 +230,7 @@ extern "C" int lbm_create(const lbm_config* cfg, lbm_handle** out) {
     if (cfg->nx < 3 || cfg->ny < 3) return fail(LBM_ERR_INVALID, "grid must be at least 3x3");
     if (cfg->collision < LBM_BGK || cfg->collision > LBM_CM_OPTIMAL) return fail(LBM_ERR_INVALID, "unknown collision operator");
     if (cfg->world < 1 || cfg->rank < 0 || cfg->rank >= cfg->world) return fail(LBM_ERR_INVALID, "bad rank/world");
+    if (cfg->world > MAX_WORLD) return fail(LBM_ERR_INVALID, "at most 64 slabs");
     if (cfg->ny / cfg->world < 2) return fail(LBM_ERR_INVALID, "each slab needs at least 2 rows");
     // host asserts of LBM::init (src/core/init/init.cuh:62-64) become error returns
     if (!(cfg->viscosity > 0.0f)) return fail(LBM_ERR_INVALID, "Negative Viscosity");
@@ -258,12 +268,12 @@ extern "C" int lbm_create(const lbm_config* cfg, lbm_handle** out) {
     if (const char* gm = getenv("LBM_B200_GRAPH")) h->graph_mode = gm[0] == '0' ? 0 : 1;
     if (const char* v = getenv("LBM_B200_IBM_ONE_BLOCK_MAX")) h->ibm_one_block_max = atoi(v);
     h->perim = 2 * cfg->nx + 2 * cfg->ny;
-    const size_t pop_floats = h->plane * h->nplanes;
-    if (cfg->ibm_mailbox_nodes < 0) { cudaStreamDestroy(h->own_stream); delete h; return fail(LBM_ERR_INVALID, "ibm_mailbox_nodes < 0"); }
+    const size_t pop_floats = (h->plane * h->nplanes + 7) / 8 * 8;     // the tail holds 8-byte counters: keep it 32-byte aligned
+    if (cfg->ibm_mailbox_nodes < 0) { lbm_destroy(h); return fail(LBM_ERR_INVALID, "ibm_mailbox_nodes < 0"); }
     h->mail_nodes = cfg->world > 1 ? (cfg->ibm_mailbox_nodes > 0 ? cfg->ibm_mailbox_nodes : 65536) : 0;
-    const size_t tail_floats = 64 + (size_t)IBM_MAIL * h->mail_nodes;         // 256 B of neighbour counters + the IBM mailbox (exported with the same IPC handle)
+    const size_t tail_floats = TAIL_FIXED_BYTES / 4 + (size_t)IBM_MAIL * h->mail_nodes;      // counters, adapter mailbox, IBM mailbox (exported with the same IPC handle)
     bool ok = dmalloc(h, &h->pop, pop_floats + tail_floats) == cudaSuccess &&
-              dmalloc(h, &h->sync_timeout, 1) == cudaSuccess &&
+              dmalloc(h, &h->sync_timeout, 1) == cudaSuccess && dmalloc(h, &h->d_net, 1) == cudaSuccess &&
               dmalloc(h, &h->ring, (size_t)2 * h->perim * Q) == cudaSuccess &&
               dmalloc(h, &h->sums, 3) == cudaSuccess && dmalloc(h, &h->avg, 3) == cudaSuccess &&
               dmalloc(h, &h->mass_acc, 1) == cudaSuccess;
@@ -272,7 +282,8 @@ extern "C" int lbm_create(const lbm_config* cfg, lbm_handle** out) {
     cudaMemsetAsync(h->pop, 0, (pop_floats + tail_floats) * sizeof(float), h->stream);
     cudaMemsetAsync(h->sync_timeout, 0, sizeof(int), h->stream);
     h->sync_flags = reinterpret_cast<unsigned long long*>(h->pop + pop_floats);     // [0..1] step counters, [2..3] IBM stage counters
-    h->ibm_mail = h->mail_nodes ? h->pop + pop_floats + 64 : nullptr;
+    h->ibm_mail = h->mail_nodes ? h->pop + pop_floats + TAIL_FIXED_BYTES / 4 : nullptr;
+    cudaMemsetAsync(h->d_net, 0, sizeof(SlabNet), h->stream);
     cudaMemsetAsync(h->ring, 0, (size_t)2 * h->perim * Q * sizeof(float), h->stream);
     float one[3] = {1.f, 1.f, 1.f};
     cudaMemcpyAsync(h->avg, one, sizeof(one), cudaMemcpyHostToDevice, h->stream);
@@ -334,8 +345,9 @@ extern "C" int lbm_set_flags(lbm_handle* h, const int32_t* flags) {
                 nbr.emplace_back(node, src);
             }
         }
+    CU(cudaStreamSynchronize(h->stream));           // steps enqueued by an asynchronous lbm_step may still read the old flags / nbr_* arrays
     if (h->nbr_nodes) { cudaFree(h->nbr_nodes); cudaFree(h->nbr_src); cudaFree(h->nbr_g); h->nbr_nodes = h->nbr_src = nullptr; h->nbr_g = nullptr; }
-    h->nbr_count = (int)nbr.size();
+    h->nbr_count = (int)nbr.size(); h->nbrg_for_ts = -1; h->pre_for_ts = -1;
     if (any || h->flags) {
         int rc = ensure_flags(h); if (rc) return rc;
         CU(cudaMemcpyAsync(h->flags, loc.data(), loc.size(), cudaMemcpyHostToDevice, h->stream));
@@ -346,8 +358,9 @@ extern "C" int lbm_set_flags(lbm_handle* h, const int32_t* flags) {
         std::vector<long long> a(nbr.size()), b(nbr.size());
         for (size_t i = 0; i < nbr.size(); i++) { a[i] = nbr[i].first; b[i] = nbr[i].second; }
         CU(dmalloc(h, &h->nbr_nodes, a.size())); CU(dmalloc(h, &h->nbr_src, a.size())); CU(dmalloc(h, &h->nbr_g, a.size() * Q));
-        CU(cudaMemcpy(h->nbr_nodes, a.data(), a.size() * 8, cudaMemcpyHostToDevice));
-        CU(cudaMemcpy(h->nbr_src, b.data(), b.size() * 8, cudaMemcpyHostToDevice));
+        CU(cudaMemcpyAsync(h->nbr_nodes, a.data(), a.size() * 8, cudaMemcpyHostToDevice, h->stream));
+        CU(cudaMemcpyAsync(h->nbr_src, b.data(), b.size() * 8, cudaMemcpyHostToDevice, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
     }
     h->segs_dirty = true;
     if (!h->h_pts.empty()) return rebuild_ibm(h);       // re-mark the IBM bit
@@ -363,18 +376,23 @@ extern "C" int lbm_set_body_force(lbm_handle* h, float fx, float fy) {
 extern "C" int lbm_set_force_field(lbm_handle* h, const float* force_aos) {
     if (!h) return fail(LBM_ERR_INVALID, "NULL handle");
     CU(cudaSetDevice(h->cfg.device));
-    h->segs_dirty = true;
-    if (!force_aos) { if (h->force_plane) { cudaFree(h->force_plane); h->force_plane = nullptr; } return LBM_OK; }
-    if (!h->force_plane) CU(dmalloc(h, &h->force_plane, (size_t)h->nloc));
-    CU(cudaMemcpy(h->force_plane, force_aos + (size_t)2 * h->y0 * h->cfg.nx, (size_t)h->nloc * sizeof(float2), cudaMemcpyHostToDevice));
+    // h->stream is a non-blocking stream: order the update after the steps an asynchronous lbm_step has enqueued on it
+    CU(cudaStreamSynchronize(h->stream));
+    if (!force_aos) {
+        if (h->force_plane) { cudaFree(h->force_plane); h->bytes -= (long long)h->nloc * (long long)sizeof(float2); h->force_plane = nullptr; h->segs_dirty = true; }
+        return LBM_OK;
+    }
+    if (!h->force_plane) { CU(dmalloc(h, &h->force_plane, (size_t)h->nloc)); h->segs_dirty = true; }
+    CU(cudaMemcpyAsync(h->force_plane, force_aos + (size_t)2 * h->y0 * h->cfg.nx, (size_t)h->nloc * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
     return LBM_OK;
 }
 
 extern "C" int lbm_set_force_field_device(lbm_handle* h, const float* d_force) {
     if (!h || !d_force) return fail(LBM_ERR_INVALID, "NULL argument");
     CU(cudaSetDevice(h->cfg.device));
-    h->segs_dirty = true;
-    if (!h->force_plane) CU(dmalloc(h, &h->force_plane, (size_t)h->nloc));
+    if (!h->force_plane) { CU(cudaStreamSynchronize(h->stream)); CU(dmalloc(h, &h->force_plane, (size_t)h->nloc)); h->segs_dirty = true; }
+    // stream-ordered behind the steps already enqueued; the caller's buffer may be reused once the call returns
     CU(cudaMemcpyAsync(h->force_plane, d_force, (size_t)h->nloc * sizeof(float2), cudaMemcpyDeviceToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return LBM_OK;
@@ -414,6 +432,11 @@ extern "C" int lbm_set_moment_sums(lbm_handle* h, const double s[3]) {
     h->launches++;
     h->avg_for_ts = h->timestep + 1;
     return LBM_OK;
+}
+
+extern "C" int lbm_adapter_sums_pending(lbm_handle* h) {
+    if (!h || h->cfg.collision != LBM_CM_OPTIMAL) return 0;
+    return h->avg_for_ts != h->timestep + 1 ? 1 : 0;
 }
 
 extern "C" int lbm_info(lbm_handle* h, lbm_info_t* o) {

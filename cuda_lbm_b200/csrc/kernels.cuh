@@ -138,6 +138,9 @@ constexpr int vec_min_blocks(int coll, bool odd) {
 #ifndef LBM_LD_HINT
 #define LBM_LD_HINT 0
 #endif
+#ifndef LBM_AVG_EARLY
+#define LBM_AVG_EARLY 1
+#endif
 #ifndef LBM_ST_HINT
 #define LBM_ST_HINT 0
 #endif
@@ -277,6 +280,13 @@ __global__ void __launch_bounds__(BX, vec_min_blocks(COLL, ODD)) step_vec_kernel
         const int x0 = xv << 2;
         const long long r0 = rowoff(p, yl);
         const int gen = p.t & 1;
+        // CM<2,OptimalAdapter>: the three grid means come from memory (the previous launch wrote them).  Their loads are issued
+        // here, in front of the population loads, so that all of them are in flight together — behind the populations they
+        // would cost a second full memory latency per thread.
+        float avg_raw[3] = {1.f, 1.f, 1.f};
+#if LBM_AVG_EARLY
+        if (COLL == C_CMOPT) { avg_raw[0] = __ldg(p.avg); avg_raw[1] = __ldg(p.avg + 1); avg_raw[2] = __ldg(p.avg + 2); }
+#endif
         V2 g[2][Q];                                   // g[h][q]: cells x0+2h, x0+2h+1 side by side (packed fp32 lanes)
         // neighbours inside the warp exchange the boundary element; a row starts at lane 0 (blockDim.x % 32 == 0)
         const bool hasL = lane > 0, hasR = lane < 31 && xv_raw < nv - 1;
@@ -330,7 +340,11 @@ __global__ void __launch_bounds__(BX, vec_min_blocks(COLL, ODD)) step_vec_kernel
         }
         float2 rho4[2], ux4[2], uy4[2];
         AdapterAvg av{};
+#if LBM_AVG_EARLY
+        if (COLL == C_CMOPT) { av.inv_rho = 1.0f / avg_raw[0]; av.inv_j = 1.0f / avg_raw[1]; av.inv_pi = 1.0f / avg_raw[2]; }
+#else
         if (COLL == C_CMOPT) av = load_adapter_avg(p.avg);
+#endif
         const Relax rx = relax_of(p);
         const bool forced = p.fx != 0.0f || p.fy != 0.0f;      // uniform body force only: everything else takes the general path
         const V2 Fx = splat<V2>(p.fx), Fy = splat<V2>(p.fy);
@@ -446,12 +460,58 @@ __global__ void __launch_bounds__(256) reduce_stage1_kernel(const float* partial
     block_sum3(partials, nblocks, (long long)blockIdx.x * 256 + threadIdx.x, (long long)gridDim.x * 256, o);
     if (threadIdx.x < 3) stage[3 * blockIdx.x + threadIdx.x] = o[threadIdx.x];
 }
-__global__ void __launch_bounds__(256) reduce_stage2_kernel(const double* stage, int n, double* sums, float* avg, double inv_n, int write_avg) {
+// ---- what a slab knows about the other slabs of the decomposition (device-resident table, built at lbm_peer_attach*):
+// every slab's adapter mailbox, IBM node mailbox and IBM stage counters, reached over NVLink peer mappings (own entries included).
+constexpr int MAX_WORLD = 64;
+struct AdpSlot { double s[3]; unsigned long long tag; };       // one slab's sums of (rho, rho|u|, |Pi|) for the step `tag`
+struct SlabNet {
+    int world, rank;
+    AdpSlot* adp[MAX_WORLD];                    // [2][MAX_WORLD] slots per slab: parity of the step x source rank; nullptr = slab not mapped
+    float* mail[MAX_WORLD];                     // IBM node mailboxes
+    unsigned long long* ibm_stage[MAX_WORLD];   // [MAX_WORLD] IBM stage counters per slab, indexed by source rank
+};
+
+// stage 2 of the reduction; with `net` it also PUBLISHES this slab's sums for step `tag` into every slab's adapter mailbox
+// (one 32-byte store per slab over NVLink, data first, tag after a system-wide fence) — the send half of the device-side
+// all-reduce of CM<2,OptimalAdapter>'s grid sums (macroscopics.cuh:161-177 is a single-GPU atomicAdd + symbol copy)
+__global__ void __launch_bounds__(256) reduce_stage2_kernel(const double* stage, int n, double* sums, float* avg, double inv_n, int write_avg,
+                                                            const SlabNet* net, unsigned long long tag) {
     double o[3];
     block_sum3(stage, n, threadIdx.x, 256, o);
     if (threadIdx.x < 3) {
         sums[threadIdx.x] = o[threadIdx.x];
         if (write_avg) avg[threadIdx.x] = (float)(o[threadIdx.x] * inv_n);
+    }
+    if (net && (int)threadIdx.x < net->world) {
+        AdpSlot* box = net->adp[threadIdx.x];
+        if (box) {
+            AdpSlot* dst = box + (tag & 1) * MAX_WORLD + net->rank;
+            dst->s[0] = o[0]; dst->s[1] = o[1]; dst->s[2] = o[2];
+            __threadfence_system();
+            *(volatile unsigned long long*)&dst->tag = tag;
+            __threadfence_system();
+        }
+    }
+}
+// the receive half: wait until every slab's sums for step `tag` have arrived in THIS slab's mailbox, add them in rank order
+// (the same order on every slab, hence the same bits) and set the grid means the step kernels read
+__global__ void __launch_bounds__(MAX_WORLD) adapter_collect_kernel(const SlabNet* net, unsigned long long tag, float* avg, double inv_n, int* timed_out) {
+    const AdpSlot* box = net->adp[net->rank] + (tag & 1) * MAX_WORLD;
+    const int r = threadIdx.x;
+    if (r < net->world) {
+        const volatile unsigned long long* tg = &box[r].tag;
+        const long long t0 = clock64();
+        while (*tg != tag) {
+            if (clock64() - t0 > 20000000000ll) { *timed_out = 3; break; }      // ~10 s: a lost slab must not hang the GPU
+            __nanosleep(100);
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+    if (r < 3) {
+        double a = 0.0;
+        for (int k = 0; k < net->world; k++) a += *(const volatile double*)&box[k].s[r];
+        avg[r] = (float)(a * inv_n);
     }
 }
 __global__ void sums_to_avg_kernel(const double* sums, float* avg, double inv_n) {
@@ -518,10 +578,9 @@ struct IbmData {
     // (IBM_MAIL floats per node), which every slab holds at the same offsets
     const int* mail_idx;                // [nnodes] mailbox slot of each node of this slab's (active) list
     float* mail;                        // this slab's mailbox
-    float* peer_mail[2];                // peer-mapped neighbours' mailboxes (nullptr = none): the owner of a node stores its state there too
-    unsigned long long* peer_flag[2];   // the neighbours' IBM stage counters this slab writes
-    volatile unsigned long long* my_flags;   // this slab's IBM stage counters [2], written by the lower / upper neighbour
-    int need[2];
+    const SlabNet* net;                 // peer-mapped slabs (nullptr = none): the owner of a node stores its state into THEIR mailboxes too
+    unsigned long long need_mask;       // ranks that own a stencil node of the bodies this slab works on: their stage counters are awaited
+    volatile unsigned long long* my_stage;   // this slab's IBM stage counters [MAX_WORLD], written by the slab of that rank
     int* timed_out;
 };
 constexpr int IBM_MAIL = 5;             // rho, u*_x, u*_y, F_x, F_y (d_force after reset_forces)
@@ -630,18 +689,21 @@ __global__ void __launch_bounds__(1024) ibm_gather_kernel(const Params p, const 
         const float v[IBM_MAIL] = {rho, us.x, us.y, F.x, F.y};
         const long long o = (long long)d.mail_idx[i] * IBM_MAIL;
 #pragma unroll
-        for (int c = 0; c < IBM_MAIL; c++) {
-            out[o + c] = v[c];
-            if (d.peer_mail[0]) d.peer_mail[0][o + c] = v[c];
-            if (d.peer_mail[1]) d.peer_mail[1][o + c] = v[c];
-        }
+        for (int c = 0; c < IBM_MAIL; c++) out[o + c] = v[c];
+        if (d.net)
+            for (int r = 0; r < d.net->world; r++) {
+                float* pm = d.net->mail[r];
+                if (!pm || r == d.net->rank) continue;
+#pragma unroll
+                for (int c = 0; c < IBM_MAIL; c++) pm[o + c] = v[c];
+            }
     }
-    if (d.peer_flag[0] || d.peer_flag[1]) {
+    if (d.net) {
         __threadfence_system();
         __syncthreads();
-        if (threadIdx.x == 0) {
-            if (d.peer_flag[0]) *(volatile unsigned long long*)d.peer_flag[0] = t;
-            if (d.peer_flag[1]) *(volatile unsigned long long*)d.peer_flag[1] = t;
+        const int r = threadIdx.x;
+        if (r < d.net->world && r != d.net->rank && d.net->ibm_stage[r]) {
+            *(volatile unsigned long long*)(d.net->ibm_stage[r] + d.net->rank) = t;
             __threadfence_system();
         }
     }
@@ -649,9 +711,9 @@ __global__ void __launch_bounds__(1024) ibm_gather_kernel(const Params p, const 
 // Stage 2, on every slab that owns part of a body: wait for the neighbours' stage counters (peer-mapped only), read the
 // complete node states from the mailbox and run the iterations redundantly — every slab of a body computes the same bits.
 __global__ void __launch_bounds__(1024) ibm_solve_kernel(const Params p, const IbmData d, unsigned long long t) {
-    if ((d.need[0] || d.need[1]) && threadIdx.x == 0) {
+    if (d.need_mask && threadIdx.x < MAX_WORLD && ((d.need_mask >> threadIdx.x) & 1ull)) {
         const long long t0 = clock64();
-        while ((d.need[0] && d.my_flags[0] < t) || (d.need[1] && d.my_flags[1] < t)) {
+        while (d.my_stage[threadIdx.x] < t) {
             if (clock64() - t0 > 20000000000ll) { *d.timed_out = 2; break; }
             __nanosleep(200);
         }
@@ -815,6 +877,33 @@ __global__ void __launch_bounds__(BX) mass_kernel(const Params p, double* out) {
     __syncthreads();
     for (int s = BX / 2; s > 0; s >>= 1) { if ((int)threadIdx.x < s) sm[threadIdx.x] += sm[threadIdx.x + s]; __syncthreads(); }
     if (threadIdx.x == 0) atomicAdd(out, sm[0]);
+}
+
+// rho and u of the LAST step rebuilt from its post-collision populations, for callers that ask for the macroscopic fields of a
+// step that was enqueued without them.  Collision conserves mass and changes momentum by a known amount dJ (Guo forcing:
+// dJ = F for BGK, CM and MRT; with the reference's swapped MRT force rows, A-D2, dJ_y = S5 F_y / 2 - F_x (1 - S5 / 2)), so
+// rho = sum f*, u* = (sum f* c - dJ) / rho, u = u* + F / (2 rho): the reference's d_rho / d_u up to fp32 round-off.
+template <bool LAST_ODD>
+__global__ void __launch_bounds__(BX) recover_macros_kernel(const Params p) {
+    const int x = blockIdx.x * BX + threadIdx.x, yl = blockIdx.y;
+    if (x >= p.nx) return;
+    float f[Q];
+    read_post_collision<LAST_ODD>(p, x, yl, f);
+    const Moments m = moments(f);
+    const long long ln = (long long)yl * p.nx + x;
+    float Fx = p.fx, Fy = p.fy;
+    if (p.force_plane) { const float2 F = p.force_plane[ln]; Fx = F.x; Fy = F.y; }
+    if (p.flags && (p.flags[ln] & FLAG_IBM)) {
+        const int k = find_sorted(p.ibm_nodes, p.ibm_count, (long long)(p.y0 + yl) * p.nx + x);
+        if (k >= 0) { const float2 F = p.ibm_force[k]; Fx = F.x; Fy = F.y; }
+    }
+    if (p.t == 0) Fx = Fy = 0.0f;            // the initial state: no collision has added momentum yet, d_u = the Init functor's u
+    float dJx = Fx, dJy = Fy;
+    if (p.coll == C_MRT && (p.quirks & QK_D2)) dJy = 0.5f * p.S[5] * Fy - Fx * (1.0f - 0.5f * p.S[5]);
+    const float jx = m.ux * m.rho - dJx, jy = m.uy * m.rho - dJy;
+    const float h = 0.5f * m.inv_rho;
+    p.rho_out[ln] = m.rho;
+    p.u_out[ln] = make_float2(fmaf(Fx, h, jx * m.inv_rho), fmaf(Fy, h, jy * m.inv_rho));
 }
 
 // ------------------------------------------------------------------ validation reductions (deterministic, fp64)

@@ -73,24 +73,22 @@ class SlabExchange:
 
 def attach_peers(engine, periodic_y, group=None):
     """Peer-mapped coupling (include/lbm_b200.h, lbm_peer_*): every rank exports the descriptor of its population
-    buffer, all-gathers them and attaches its two y-neighbours.  Afterwards the fused kernel reads / writes the
-    neighbour's edge rows over NVLink itself and `engine.step(n)` needs no host-side exchange."""
+    buffer, all-gathers them and maps ALL slabs (lbm_peer_attach_all; the two y-neighbours among them are attached as such).
+    Afterwards the fused kernel reads / writes the neighbour's edge rows over NVLink itself, CM<2,OptimalAdapter>'s grid sums
+    are all-reduced on the device, bodies may span any number of slabs, and `engine.step(n)` needs no host-side exchange."""
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     descs = [None] * world
     dist.all_gather_object(descs, engine.peer_export(), group=group)
-    lo, hi = neighbours(rank, world, periodic_y)
-    if lo is not None:
-        engine.peer_attach(0, descs[lo])
-    if hi is not None:
-        engine.peer_attach(1, descs[hi])
+    engine.peer_attach_all(descs)
     dist.barrier(group=group)
-    return lo, hi
+    return neighbours(rank, world, periodic_y)
 
 
 class SlabSolver:
     """The solver loop of one rank.  mode "direct": neighbours' edge rows are peer-mapped (NVLink loads/stores inside the
-    fused kernel, device-side step handshake) and n steps are enqueued at once; mode "nccl": lbm_step one step at a
-    time with packed halo rows sent through torch.distributed in between."""
+    fused kernel, device-side step handshake, device-side all-reduce of the adapter sums) and n steps are enqueued at once;
+    mode "nccl": lbm_step one step at a time with packed halo rows (and IBM node states, adapter sums) sent through
+    torch.distributed in between."""
 
     def __init__(self, engine, nx, periodic_y, device, optimal_adapter=False, adapter_exact=True, group=None, mode="nccl"):
         self.e = engine
@@ -138,22 +136,25 @@ class SlabSolver:
         if self.world == 1 or (self.mode == "direct" and not self.optimal):
             self.e.run_from_host(rho_ptr, u_ptr, n, rho_out_ptr, u_out_ptr)
             return
+        # OptimalAdapter needs grid sums (no band pipeline), or the halo coupling: the three calls
         self.e.init_fields_local(rho_ptr, u_ptr)
         self.barrier_after_init()
         self.step(n, macroscopics=True)
         self.e.macroscopics_into(rho_out_ptr, u_out_ptr)
 
     def step(self, n=1, macroscopics=False):
-        if self.world == 1 or (self.mode == "direct" and not self.optimal):
+        if self.world == 1 or self.mode == "direct":
+            # peer-mapped slabs: halo rows, IBM node states and the adapter's grid sums all travel inside the kernels
             self.e.step(n, macroscopics=macroscopics)
             return
         for i in range(n):
             need = self.e.next_step_needs_halo()
             if need:
                 self.x.exchange("pre")
-            if self.mode != "direct":
-                self._exchange_ibm()
-            if self.optimal and self.exact:
+            self._exchange_ibm()
+            # exact mode: the grid sums of this step's post-stream state; lagged mode: only while no previous step has produced
+            # them (first step after init / restart / set_populations)
+            if self.optimal and (self.exact or getattr(self.e, "adapter_sums_pending", lambda: False)()):
                 self.e.adapter_prepass()
                 self._allreduce_sums()
             self.e.step(1, macroscopics=macroscopics and i == n - 1)

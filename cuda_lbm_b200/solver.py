@@ -179,6 +179,12 @@ class Engine:
     def adapter_prepass(self):
         check(lib().lbm_adapter_prepass(self._h))
 
+    def adapter_sums_pending(self):
+        return bool(lib().lbm_adapter_sums_pending(self._h))
+
+    def recover_macroscopics(self):
+        check(lib().lbm_recover_macroscopics(self._h))
+
     # --- validation on the device (this slab's sums; add them over slabs) ---
     def velocity_error_sums(self, d_u_ref_ptr):
         o = (C.c_double * 2)()
@@ -217,6 +223,11 @@ class Engine:
     def peer_attach(self, side, desc):
         buf = (C.c_ubyte * capi.PEER_DESC_BYTES).from_buffer_copy(desc)
         check(lib().lbm_peer_attach(self._h, side, buf))
+
+    def peer_attach_all(self, descs):
+        """descs: the peer_export() bytes of ALL slabs, indexed by rank."""
+        buf = (C.c_ubyte * (capi.PEER_DESC_BYTES * len(descs))).from_buffer_copy(b"".join(descs))
+        check(lib().lbm_peer_attach_all(self._h, buf, len(descs)))
 
     def peer_detach(self):
         check(lib().lbm_peer_detach(self._h))

@@ -336,6 +336,9 @@ public:
     // LBM::update_macroscopics() — src/core/lbm.cuh:148-154
     void update_macroscopics() {
         flush(true);        // no-op after finish_step(): the macroscopics of the current step are already on the device
+        // the step was closed without them (increase_ts() of the next step came first): rebuilt from its populations, so that —
+        // as in the reference, whose d_rho / d_u are always current — this call is legal at any point of the driver loop
+        LBM_B200_CALL(lbm_recover_macroscopics(h));
         update_ts = timestep;
         LBM_B200_CALL(lbm_get_macroscopics(h, h_rho.data(), h_u.data()));
     }
@@ -343,12 +346,14 @@ public:
     // device views of rho[node] and u[node*2+c], valid until the next step (d_rho / d_u of the reference)
     float* get_rho() {
         flush(true);
+        LBM_B200_CALL(lbm_recover_macroscopics(h));
         const float *r = nullptr, *u = nullptr;
         LBM_B200_CALL(lbm_get_macroscopics_device(h, &r, &u));
         return const_cast<float*>(r);
     }
     float* get_u() {
         flush(true);
+        LBM_B200_CALL(lbm_recover_macroscopics(h));
         const float *r = nullptr, *u = nullptr;
         LBM_B200_CALL(lbm_get_macroscopics_device(h, &r, &u));
         return const_cast<float*>(u);
@@ -371,6 +376,7 @@ public:
     template <typename Scenario>
     float l2_error_device() {
         flush(true);
+        LBM_B200_CALL(lbm_recover_macroscopics(h));
         const long long n = (long long)NX * NY;
         float2* d_ref = nullptr;
         checkCudaErrors(cudaMalloc(&d_ref, (size_t)n * sizeof(float2)));
@@ -385,7 +391,7 @@ public:
     // extension: checkpoint / restart of the population state (lbm_checkpoint_write / lbm_checkpoint_read).  load_checkpoint
     // is called after allocate<S>() and init<S>() (which set flags, forces and bodies) and continues bit-identically.
     void save_checkpoint(const std::string& path) {
-        flush(false);
+        flush(true);      // a pending step is closed WITH its rho / u: a following save_vtk() / update_macroscopics() finds them
         LBM_B200_CALL(lbm_checkpoint_write(h, path.c_str()));
     }
     template <typename Scenario>
@@ -401,19 +407,19 @@ public:
 
     // grid means of rho, rho|u|, |Pi| that the last CM<2,OptimalAdapter> step used (the reference's d_moment_avg)
     MomentInfo moment_avg() {
-        flush(false);
+        flush(true);      // a pending step is closed WITH its rho / u: a following save_vtk() / update_macroscopics() finds them
         float a[3];
         LBM_B200_CALL(lbm_moment_avg(h, a));
         return MomentInfo{a[0], a[1], a[2]};
     }
     double total_mass() {
-        flush(false);
+        flush(true);      // a pending step is closed WITH its rho / u: a following save_vtk() / update_macroscopics() finds them
         double m = 0.0;
         LBM_B200_CALL(lbm_total_mass(h, &m));
         return m;
     }
     void synchronize() {
-        flush(false);
+        flush(true);      // a pending step is closed WITH its rho / u: a following save_vtk() / update_macroscopics() finds them
         LBM_B200_CALL(lbm_sync(h));
     }
     lbm_handle* handle() { return h; }

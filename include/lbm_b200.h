@@ -189,6 +189,11 @@ int lbm_reserve_macroscopics(lbm_handle* h);
 /* Same, leaving the result in device memory owned by the handle (valid until the next step). */
 int lbm_get_macroscopics_device(lbm_handle* h, const float** d_rho_local, const float** d_u_aos_local);
 
+/* rho / u of the current step for callers that enqueued it with plain lbm_step: rebuilt from the post-collision populations
+ * (collision conserves mass and adds a known momentum), i.e. the reference's d_rho / d_u — which are always current there,
+ * src/core/lbm.cuh:148-154 — up to fp32 round-off.  No-op when the step already stored them. */
+int lbm_recover_macroscopics(lbm_handle* h);
+
 /* Sum of all populations of this slab in fp64 (mass diagnostic; no reference counterpart). */
 int lbm_total_mass(lbm_handle* h, double* out);
 /* d_moment_avg — src/core/lbm.cuh:25-31: grid means of rho, rho|u|, |Pi| used by the last step (this slab's sums / global N). */
@@ -198,6 +203,9 @@ int lbm_moment_avg(lbm_handle* h, float out[3]);
  * global sums back with lbm_set_moment_sums before lbm_step.  With LBM_ADAPTER_LAGGED the sums come out of
  * the step itself and only the get / all-reduce / set part is needed. */
 int lbm_adapter_prepass(lbm_handle* h);
+/* 1 when the next lbm_step of a CM<2,OptimalAdapter> slab still needs global sums handed in (several slabs, host-side all-reduce):
+ * always in LBM_ADAPTER_EXACT mode, and in LBM_ADAPTER_LAGGED mode for the first step after init / restart / lbm_set_populations. */
+int lbm_adapter_sums_pending(lbm_handle* h);
 int lbm_set_moment_sums(lbm_handle* h, const double sums[3]);
 int lbm_get_moment_sums(lbm_handle* h, double sums[3]);
 
@@ -249,8 +257,8 @@ int lbm_halo_unpack_post(lbm_handle* h, int side, const float* d_buf);
  * states for the NEXT step into a device buffer of lbm_ibm_exchange_floats floats (zeros for nodes other slabs own),
  * the caller all-reduces (sum) the buffer over ALL slabs, lbm_ibm_unpack hands it back, then lbm_step.  (After the
  * pre-step halo exchange; before lbm_adapter_prepass.)  With peer-mapped neighbours none of this is needed: the owners
- * store the states into their neighbours' mailboxes over NVLink inside the pre-pass kernel — a body may then span a
- * slab and its two neighbours, not more.  lbm_ibm_exchange_floats is 0 when nothing has to be exchanged. */
+ * store the states into the mailboxes of the slabs they have mapped over NVLink inside the pre-pass kernel — a body may then span
+ * a slab and its two neighbours (lbm_peer_attach) or any number of slabs (lbm_peer_attach_all).  lbm_ibm_exchange_floats is 0 when nothing has to be exchanged. */
 int lbm_ibm_exchange_floats(lbm_handle* h, int64_t* out);
 int lbm_ibm_pack(lbm_handle* h, float* d_buf);
 int lbm_ibm_unpack(lbm_handle* h, const float* d_buf);
@@ -267,6 +275,12 @@ int lbm_ibm_unpack(lbm_handle* h, const float* d_buf);
 #define LBM_PEER_DESC_BYTES 128
 int lbm_peer_export(lbm_handle* h, void* desc);
 int lbm_peer_attach(lbm_handle* h, int side, const void* desc);
+/* Same for the whole decomposition in one call: descs = the descriptors of ALL slabs, indexed by rank (world x LBM_PEER_DESC_BYTES).
+ * Maps every other slab and attaches the two y-neighbours.  With all slabs mapped, (1) CM<2,OptimalAdapter> needs no host
+ * all-reduce any more: each slab's sums of rho, rho|u|, |Pi| are stored into every slab's mailbox over NVLink by the reduction
+ * kernel and added there in rank order (identical bits on every slab), so lbm_step(h, n) runs n steps on its own; (2) a body may
+ * span any number of slabs. */
+int lbm_peer_attach_all(lbm_handle* h, const void* descs, int32_t count);
 int lbm_peer_detach(lbm_handle* h);
 
 /* Pinned host memory helpers for callers that want full-speed host<->device copies. */

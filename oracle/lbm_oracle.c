@@ -757,6 +757,15 @@ int oracle_num_threads(void) {
 #endif
 }
 
+/* torchrun exports OMP_NUM_THREADS=1 to its workers: the timed CPU legs of bench.py ask for the host's cores explicitly */
+void oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 /* ------------------------------------------------------------------ scenario functors (host side) */
 /* TaylorGreenInit::operator()  taylorGreenFunctors.cuh:25-47  (u_max already divided by SCALE, :11-13) */
 void oracle_init_taylor_green(int nx, int ny, float nu, float u_max, float *rho, float *u_aos) {

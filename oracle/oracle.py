@@ -56,6 +56,7 @@ def lib():
         L.oracle_total_mass.argtypes = [C.c_void_p]
         L.oracle_total_mass.restype = C.c_double
         L.oracle_num_threads.restype = C.c_int
+        L.oracle_set_num_threads.argtypes = [C.c_int]
         L.oracle_init_taylor_green.argtypes = [C.c_int, C.c_int, C.c_float, C.c_float, fp, fp]
         L.oracle_taylor_green_analytic.argtypes = [C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, fp]
         L.oracle_poiseuille_force.argtypes = [C.c_float, C.c_float, C.c_int]
@@ -178,3 +179,11 @@ def create_cylinder(cx, cy, r, num_pts=16):
 
 def num_threads():
     return lib().oracle_num_threads()
+
+
+def set_num_threads(n=None):
+    """OpenMP threads of the following oracle calls; None = every core this process may run on (torchrun sets OMP_NUM_THREADS=1)."""
+    if n is None:
+        n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    lib().oracle_set_num_threads(int(n))
+    return num_threads()

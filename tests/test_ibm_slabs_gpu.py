@@ -68,6 +68,19 @@ def test_peer_mapped_slabs_with_bodies_match_single_domain(bodies, world, coll, 
     assert np.abs(rho_s - rho_1).max() <= tol and np.abs(u_s - u_1).max() <= tol
 
 
+@pytest.mark.parametrize("bodies,world,coll,chunk", [(BIG, 6, cases.MRT, 7), (THREE, 5, cases.CM_OPT, 3), (BIG, 4, cases.BGK, 2)])
+def test_all_mapped_slabs_carry_a_body_over_any_number_of_slabs(bodies, world, coll, chunk):
+    """lbm_peer_attach_all: the owner of a stencil node stores its state into EVERY slab's mailbox, a slab that works on a body
+    waits for the stage counters of all the slabs that own part of it — BIG spans four of the six 8-row slabs."""
+    case = _case("ibm_slabs_all", coll, bodies())
+    nsteps = 7
+    rho_s, u_s, f_s = _run_slabs(case, world, nsteps, direct="all", chunk=chunk)
+    (rho_1, u_1), f_1, _ = _single(case, nsteps)
+    tol = 0.0 if coll != cases.CM_OPT else 2e-7
+    assert np.abs(f_s - f_1).max() <= tol, np.abs(f_s - f_1).max()
+    assert np.abs(rho_s - rho_1).max() <= tol and np.abs(u_s - u_1).max() <= tol
+
+
 def test_body_over_three_slabs_is_refused_by_the_peer_mapped_coupling():
     """Peer-mapped slabs reach their two neighbours only: the outer slabs of a three-slab body cannot see the far one."""
     import cuda_lbm_b200 as L

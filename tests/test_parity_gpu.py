@@ -130,6 +130,9 @@ def _run_slabs(case, world, nsteps, adapter_mode=0, direct=False, chunk=1):
     if direct:
         descs = [e.peer_export() for e in engs]
         for r, e in enumerate(engs):
+            if direct == "all":         # every slab maps every other one: adapter sums and IBM node states travel on the device
+                e.peer_attach_all(descs)
+                continue
             for side, q in ((0, r - 1), (1, r + 1)):
                 if 0 <= q < world or py0:
                     e.peer_attach(side, descs[q % world])
@@ -177,7 +180,7 @@ def _run_slabs(case, world, nsteps, adapter_mode=0, direct=False, chunk=1):
         for e in engs:
             e.sync()
 
-    if direct and case.coll != cases.CM_OPT:
+    if direct and (case.coll != cases.CM_OPT or direct == "all"):
         done = 0
         while done < nsteps:
             n = min(chunk, nsteps - done)
@@ -247,6 +250,27 @@ def test_peer_mapped_slabs_match_single_domain(name, world, chunk):
     f_1 = e.populations()
     e.close()
     tol = 0.0 if case.coll != cases.CM_OPT else 2e-7
+    assert np.abs(f_s - f_1).max() <= tol, np.abs(f_s - f_1).max()
+    assert np.abs(rho_s - rho_1).max() <= tol and np.abs(u_s - u_1).max() <= tol
+
+
+@pytest.mark.parametrize("name,world,chunk,mode", [("g_tg_cmopt", 2, 3, 0), ("g_lid_cmopt", 3, 7, 0), ("g_lid_cmopt", 4, 2, 1), ("g_tg_cmopt", 3, 7, 1),
+                                                   ("g_lid_cm", 4, 7, 0)])
+def test_all_mapped_slabs_run_the_optimal_adapter_without_the_host(name, world, chunk, mode):
+    """lbm_peer_attach_all: every slab maps every other one.  CM<2,OptimalAdapter>'s grid sums are then all-reduced on the device
+    (each slab's reduction kernel stores its three sums into every slab's mailbox over the peer mapping, a collect kernel adds
+    them in rank order), so lbm_step(h, n) runs n steps per call in both adapter modes — no host all-reduce in between."""
+    case = cases.BY_NAME[name]
+    nsteps = 7
+    rho_s, u_s, f_s = _run_slabs(case, world, nsteps, adapter_mode=mode, direct="all", chunk=chunk)
+    e = make_engine(case, adapter_mode=mode)
+    e.init_fields(*case.init_fields())
+    e.step(nsteps, macroscopics=True)
+    rho_1, u_1 = e.macroscopics()
+    f_1 = e.populations()
+    e.close()
+    tol = 0.0 if case.coll != cases.CM_OPT else 2e-7
+    assert np.isfinite(f_s).all()
     assert np.abs(f_s - f_1).max() <= tol, np.abs(f_s - f_1).max()
     assert np.abs(rho_s - rho_1).max() <= tol and np.abs(u_s - u_1).max() <= tol
 
