@@ -7,7 +7,7 @@
 
 Workload (config.workload): BASELINE.json configs[3], the configuration its metric and targets are quoted on —
 Taylor-Green vortex, D2Q9, BGK, 32768 x 32768, periodic, y-slab decomposed over N GPUs of one box (strong
-scaling: the grid is fixed, each rank owns 32768/N rows).  It fits one B200 (38.7 GB of populations).
+scaling: the grid is fixed, each rank owns 32768/N rows; --rows-per-gpu R = weak scaling).  It fits one B200 (38.7 GB of populations).
 A "step" is one time step of the whole grid = one launch of the fused kernel per rank (+ halo rows on odd steps).
 
   value    MLUPS with the populations resident in HBM, timed with CUDA events on the launching stream, max over ranks
@@ -16,7 +16,14 @@ A "step" is one time step of the whole grid = one launch of the fused kernel per
            save interval, src/main.cu:77-147).  lbm_run_from_host per rank (one call, copies and kernels pipelined over
            row bands; peer-mapped slabs synchronise their faces level by level on the device)
   roofline 72 B per cell-update (9 fp32 reads + 9 writes) / measured kernel time vs MEASURED_PEAKS.json
-  cpu_baseline  the CPU oracle (oracle/lbm_oracle.c, OpenMP) on a bounded sample, rank 0, N = 1 only
+  check    correctness of the state the timed region left behind, computed outside it: relative L2 error of u against the
+           analytic Taylor-Green decay (the reference's metric, taylorGreenScenario.cuh:59-88; sums taken on the device and
+           all-reduced over the ranks) and the mass drift since init
+  cpu_baseline  the CPU oracle (oracle/lbm_oracle.c, OpenMP) on a bounded sample, rank 0
+  reference_cuda (N = 1)  the reference's OWN CUDA solver (oracle/_ref/bin/t_tg_bgk_8192, built from its sources by oracle/build_ref.sh)
+           on the largest Taylor-Green box it can hold, timed by its own CUDA events outside this script's timed region
+  configs  (N = 1)  the other four BASELINE.json configurations through the C++ ScenarioTrait / LBM<2> header shim
+           (examples/_bin/ex_c*, built from examples/main.cu) with the reference's CUDA solver on the same scenario beside each
 
 --impl reference: the reference's algorithm on the box's host cores.  The reference's solver is CUDA-only; its
 CPU form is the statement-by-statement restatement in oracle/ (kind "port"), run with all host threads on a
@@ -25,8 +32,10 @@ bounded sample (a 4096 x 4096 sub-grid of the same workload per step).
 import argparse
 import json
 import os
+import re
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -37,6 +46,8 @@ NX = NY = 32768
 NU = 1.0 / 6.0
 U0 = 0.04 / 256.0          # TaylorGreenInit: u_max / SCALE, SCALE = NX/128 (taylorGreenFunctors.cuh:11-13, defines.hpp:20-23)
 BYTES_PER_UPDATE = 72.0
+EX = os.path.join(ROOT, "examples", "_bin")
+REF = os.path.join(ROOT, "oracle", "_ref", "bin")
 
 
 def measured_peak():
@@ -94,9 +105,10 @@ class ClockSampler:
 
 
 def cpu_oracle_mlups(n, steps, warm=1):
-    """TG BGK on an n x n periodic grid with the CPU oracle, all OpenMP threads.  Returns (MLUPS, threads, seconds)."""
+    """TG BGK on an n x n periodic grid with the CPU oracle on every core this process may use.  Returns (MLUPS, threads, seconds)."""
     from oracle import oracle as O
     import numpy as np
+    threads = O.set_num_threads()           # torchrun exports OMP_NUM_THREADS=1 to its workers: ask for the host's cores explicitly
     rho, u = O.taylor_green_init(n, n, NU, 0.04 / (n / 128.0))
     o = O.Oracle(n, n, coll=O.BGK, viscosity=NU, periodic=(True, True), u_max=0.04)
     o.init(rho, u)
@@ -105,7 +117,7 @@ def cpu_oracle_mlups(n, steps, warm=1):
     o.step(steps)
     dt = time.perf_counter() - t0
     assert np.isfinite(o.macroscopics()[0]).all()
-    return n * n * steps / dt / 1e6, O.num_threads(), dt
+    return n * n * steps / dt / 1e6, threads, dt
 
 
 def run_reference(args):
@@ -113,9 +125,10 @@ def run_reference(args):
     if rank != 0:
         return
     n = 4096
-    mlups_w, threads, _ = cpu_oracle_mlups(n, max(1, args.warmup), warm=0)
+    cpu_oracle_mlups(n, max(1, args.warmup), warm=0)
     mlups, threads, dt = cpu_oracle_mlups(n, args.steps, warm=0)
-    sample = f"Taylor-Green BGK {n}x{n} sub-grid per step (bounded sample of the {NX}x{NY} workload), {args.steps} steps, {threads} OpenMP threads"
+    sample = (f"Taylor-Green BGK {n}x{n} sub-grid per step (bounded sample of the {NX}x{NY} workload: MLUPS is per cell), {args.steps} steps, "
+              f"{threads} OpenMP threads (set explicitly; {os.cpu_count()} host cores)")
     line = {"impl": "reference", "metric": "MLUPS", "value": mlups, "unit": "MLUPS", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -125,6 +138,74 @@ def run_reference(args):
             "e2e": {"value": mlups, "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------ the reference's CUDA build and the other BASELINE configurations
+def reference_cuda_mlups(binary, steps, timeout=600):
+    """Runs one of the reference's own CUDA solver binaries (oracle/_ref/bin) and returns its REF_MLUPS line as a dict, or None."""
+    path = os.path.join(REF, binary)
+    if not os.path.exists(path):
+        return None
+    with tempfile.TemporaryDirectory() as tmp:
+        try:
+            r = subprocess.run([path, str(steps), tmp, "x"], capture_output=True, text=True, timeout=timeout)
+        except Exception as ex:  # noqa: BLE001
+            return {"binary": binary, "error": str(ex)[:200]}
+    m = re.search(r"REF_MLUPS ([0-9.]+) steps (\d+) ms_per_step ([0-9.]+) nx (\d+) ny (\d+)", r.stdout)
+    if not m:
+        return {"binary": binary, "error": (r.stdout[-200:] + r.stderr[-200:]).strip()}
+    return {"binary": "oracle/_ref/bin/" + binary, "grid": [int(m.group(4)), int(m.group(5))], "mlups": float(m.group(1)),
+            "ms_per_step": float(m.group(3)), "timed_steps": int(m.group(2)),
+            "what": "the reference's own translation units (src/core, src/IBM) compiled for sm_100a by oracle/build_ref.sh; median-free mean of its per-step CUDA-event times"}
+
+
+# name -> (shim binary, reference binary, nx, ny, operator, warm-up steps, timed steps, reference steps, description)
+CONFIGS = {
+    "c1": ("ex_c1_tg_256", "c1_tg_bgk_256", 256, 256, "BGK", 64, 4000, 200, "Taylor-Green 256x256 BGK (configs[0])"),
+    "c2": ("ex_c2_pois_1024x256", "c2_pois_mrt_1024x256", 1024, 256, "MRT", 64, 4000, 200, "Poiseuille 1024x256 MRT, body force, bounce-back walls (configs[1])"),
+    "c3": ("ex_c3_lid_4096", "c3_lid_cmopt_4096", 4096, 4096, "CM<OptimalAdapter> (exact grid means)", 16, 48, 40,
+           "lid-driven cavity 4096x4096 CM<OptimalAdapter> (configs[2]); run inside the window in which the reference's adapter keeps the field finite"),
+    "c3_lagged": ("ex_c3_lid_4096", None, 4096, 4096, "CM<OptimalAdapter> (grid means of the previous step)", 16, 48, 0,
+                  "configs[2] with LBM_ADAPTER_LAGGED (72 B/cell; deviation from the exact mode: tests/test_reference_fullsize_gpu.py)"),
+    "c5": ("ex_c5_cyl_8192x2048", "c5_cyl_ibm_mrt_8192x2048", 8192, 2048, "MRT + IBM (256 markers)", 32, 400, 60,
+           "flow past cylinder 8192x2048 MRT, IBM direct forcing (configs[4])"),
+}
+
+
+def run_config(name, peak):
+    shim, ref, nx, ny, op, warm, steps, ref_steps, what = CONFIGS[name]
+    path = os.path.join(EX, shim)
+    if not os.path.exists(path):
+        return {"name": name, "unavailable": f"examples/_bin/{shim} not built"}
+    env = dict(os.environ)
+    if name == "c3_lagged":
+        env["LBM_B200_ADAPTER"] = "1"
+    with tempfile.TemporaryDirectory() as tmp:
+        try:
+            r = subprocess.run([path, "--steps", str(steps), "--save-int", str(steps), "--warmup", str(warm), "--fast"], cwd=tmp, env=env,
+                               capture_output=True, text=True, timeout=600)
+        except Exception as ex:  # noqa: BLE001
+            return {"name": name, "error": str(ex)[:200]}
+    m = re.search(r"SHIM_RESULT (.*)", r.stdout)
+    if not m:
+        return {"name": name, "error": (r.stdout[-300:] + r.stderr[-300:]).strip()}
+    res = dict(kv.split("=") for kv in m.group(1).split())
+    mlups, mass = float(res["mlups"]), float(res["mass_per_node"])
+    cells = nx * ny
+    out = {"name": name, "workload": what, "nx": nx, "ny": ny, "collision": op, "warmup_steps": warm, "steps": steps,
+           "mlups": mlups, "ms_per_step": float(res["ms_per_step"]),
+           "finite": bool(mass == mass and abs(mass) < 1e30 and float(res["sum_u2"]) == float(res["sum_u2"])), "mass_per_node": mass,
+           "api": "examples/main.cu over the LBM<2> / ScenarioTrait header shim (include/cuda-lbm), LBM::run<Scenario>(n)"}
+    # the HBM roofline applies where the populations (36 B/cell) do not fit the 126 MB L2
+    out["roofline_frac"] = (BYTES_PER_UPDATE * mlups * 1e6 / 1e9 / peak) if 36.0 * cells > 4 * 126e6 else None
+    if out["roofline_frac"] is None:
+        out["roofline_note"] = "populations are L2-resident: launch / latency bound, no HBM roofline claim"
+    if ref:
+        rc = reference_cuda_mlups(ref, ref_steps)
+        out["reference_cuda"] = rc
+        if rc and "mlups" in rc:
+            out["speedup_vs_reference_cuda"] = mlups / rc["mlups"]
+    return out
 
 
 def main():
@@ -140,6 +221,7 @@ def main():
                     help="weak scaling: ny = rows-per-gpu * N (BASELINE configs[3]: 32768 x 4096*G slabs); default 0 = strong scaling on the fixed grid")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the N = 1 legs that run the other BASELINE configurations and the reference's CUDA build")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -167,6 +249,7 @@ def main():
         ny, scaling = args.rows_per_gpu * world, "weak"
     coll = {"BGK": L.BGK, "MRT": L.MRT, "CM": L.CM, "CM_OPT": L.CM_OPTIMAL}[args.collision]
     scale = nx / 128.0
+    u0 = 0.04 / scale
     eng = L.Engine(nx, ny, collision=coll, viscosity=NU, periodic=(True, True), u_max=0.04, device=local, rank=rank, world=world,
                    adapter_mode=L.ADAPTER_LAGGED)
     # one explicit stream for the engine's kernels, the NCCL halo traffic and the timing events
@@ -183,16 +266,23 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def max_over_ranks(v):
+    def reduce_ranks(vals, op):
         if world == 1:
-            return v
-        t = torch.tensor([v], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+            return [float(v) for v in vals]
+        t = torch.tensor(list(vals), dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=op)
+        return [float(v) for v in t.tolist()]
+
+    def max_over_ranks(v):
+        return reduce_ranks([v], dist.ReduceOp.MAX if world > 1 else None)[0]
+
+    def sum_over_ranks(vals):
+        return reduce_ranks(vals, dist.ReduceOp.SUM if world > 1 else None)
 
     # ---------------- device-resident measurement ----------------
-    eng.init_taylor_green(NU, 0.04 / scale)
+    eng.init_taylor_green(NU, u0)
     solver.barrier_after_init()
+    mass0 = sum_over_ranks([eng.total_mass()])[0]
     solver.step(args.warmup)
     barrier()
     l0 = eng.info().kernel_launches
@@ -208,28 +298,40 @@ def main():
     ms = max_over_ranks(e0.elapsed_time(e1))
     clk = clocks.stop() if rank == 0 else None
     launches = eng.info().kernel_launches - l0
-    mass = eng.total_mass()
-    assert np.isfinite(mass), "non-finite state after the timed region"
     mlups = nx * ny * args.steps / (ms * 1e-3) / 1e6
     # dominant kernel = the fused step kernel: one launch per step per rank over nloc cells
     kern_ms = ms / args.steps
     achieved = BYTES_PER_UPDATE * nloc / (kern_ms * 1e-3) / 1e9
     peak, peak_src = measured_peak()
-    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of this very command
-    # (profiles/r01_ncu_bench_kernel.md, second capture: 77.261 GB odd phase, 77.259 GB even phase); other sizes were not captured
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch: a CITATION of the ncu --set full capture of this command at N = 1
+    # (profiles/r01_ncu_bench_kernel.md: 77.261 GB odd phase, 77.259 GB even phase), scaled by the rows this rank owns; not re-measured per run
     traffic = 77.260e9 * (nloc / float(NX * NY)) if (nx == NX and args.collision == "BGK") else None
+
+    # ---------------- correctness of the state the timed region left behind (outside the timed region) ----------------
+    # one more step that also stores rho / u, then the reference's Taylor-Green metric with both sums taken on the device
+    # (lbm_taylor_green_error_sums, taylorGreenScenario.cuh:59-88) and the mass, all-reduced over the ranks
+    solver.step(1, macroscopics=True)
+    t_total = args.warmup + args.steps + 1
+    s = sum_over_ranks(list(eng.taylor_green_error_sums(NU, u0, float(t_total))))
+    mass1 = sum_over_ranks([eng.total_mass()])[0]
+    finite = bool(np.isfinite(s).all() and np.isfinite(mass1) and s[1] > 0)
+    check = {"finite": finite, "steps_total": t_total,
+             "tg_l2_error_pct": (100.0 * (s[0] / s[1]) ** 0.5) if finite else None,
+             "mass_per_cell": mass1 / (float(nx) * ny), "mass_rel_drift": mass1 / mass0 - 1.0,
+             "how": "lbm_taylor_green_error_sums + lbm_total_mass after the timed region, summed over the ranks (fp64); the reference's stale rest population (A-D1, reproduced) makes mass drift at the 1e-6 level"}
+    assert finite, "non-finite state after the timed region"
 
     # ---------------- end to end through the public API with host buffers ----------------
     e2e = None
     if not args.no_e2e:
-        from cuda_lbm_b200._capi import lib, check
+        from cuda_lbm_b200._capi import lib, check as chk
         import ctypes as C
         h_rho, h_u = C.c_void_p(), C.c_void_p()
-        check(lib().lbm_host_alloc(C.byref(h_rho), nloc * 4))
-        check(lib().lbm_host_alloc(C.byref(h_u), nloc * 8))
+        chk(lib().lbm_host_alloc(C.byref(h_rho), nloc * 4))
+        chk(lib().lbm_host_alloc(C.byref(h_u), nloc * 8))
         # host-resident input: the Init functor's rho,u for this slab, produced once outside the timed region
-        check(lib().lbm_reserve_macroscopics(eng._h))
-        eng.init_taylor_green(NU, 0.04 / scale)
+        chk(lib().lbm_reserve_macroscopics(eng._h))
+        eng.init_taylor_green(NU, u0)
         eng.macroscopics_into(h_rho.value, h_u.value)
         solver.barrier_after_init()
         barrier()
@@ -244,31 +346,45 @@ def main():
         except L.LbmError as ex:        # never lose the bench line over the e2e leg: every rank falls back together
             failed, api = 1.0, f"fallback after: {ex}"
         if max_over_ranks(failed) > 0:
-            eng.init_taylor_green(NU, 0.04 / scale)
+            eng.init_taylor_green(NU, u0)
             eng.macroscopics_into(h_rho.value, h_u.value)
             solver.barrier_after_init()
             barrier()
             t0 = time.perf_counter()
-            check(lib().lbm_init_fields_local(eng._h, h_rho, h_u))
+            chk(lib().lbm_init_fields_local(eng._h, h_rho, h_u))
             solver.barrier_after_init()
             solver.step(args.steps, macroscopics=True)
             eng.macroscopics_into(h_rho.value, h_u.value)
             api = "lbm_init_fields_local + lbm_step_with_macroscopics + lbm_get_macroscopics (" + (api or "another rank's lbm_run_from_host failed") + ")"
         barrier()
         dt = max_over_ranks(time.perf_counter() - t0)
+        # the result in the HOST buffers is what the user gets: check it too (mean of rho over this rank's rows, summed over ranks)
+        h_sum = float(np.ctypeslib.as_array(C.cast(h_rho, C.POINTER(C.c_float)), shape=(nloc,)).sum(dtype=np.float64))
+        h_mean = sum_over_ranks([h_sum])[0] / (float(nx) * ny)
         e2e = {"value": nx * ny * args.steps / dt / 1e6, "unit": "MLUPS",
                "h2d_bytes_per_step": 12.0 * nloc / args.steps, "d2h_bytes_per_step": 12.0 * nloc / args.steps,
-               "segment": f"pinned host rho,u -> H2D -> {args.steps} steps -> D2H rho,u ({12 * nloc / 1e9:.2f} GB each way per rank)", "api": api,
-               "seconds": dt}
+               "segment": f"pinned host rho,u -> H2D -> {args.steps} steps -> D2H rho,u ({12 * nloc / 1e9:.2f} GB each way per rank; output written over the input buffers)", "api": api,
+               "seconds": dt, "host_result_mean_rho": h_mean}
         lib().lbm_host_free(h_rho)
         lib().lbm_host_free(h_u)
+    eng.close()
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
+    if rank == 0 and not args.no_cpu:
         n = 2048
         v, threads, dt = cpu_oracle_mlups(n, 60)
         cpu = {"value": v, "unit": "MLUPS", "cores": threads, "kind": "port",
                "sample": f"CPU oracle (oracle/lbm_oracle.c, OpenMP x{threads}), Taylor-Green BGK {n}x{n}, 60 steps, {dt:.1f} s"}
+
+    # ---------------- N = 1: the reference's CUDA solver and the other BASELINE configurations, outside every timed region ----------------
+    ref_cuda, configs = None, None
+    if rank == 0 and world == 1 and not args.no_configs:
+        ref_cuda = reference_cuda_mlups("t_tg_bgk_8192", 40)
+        if ref_cuda and "mlups" in ref_cuda:
+            ref_cuda["note"] = ("Taylor-Green BGK on the largest square box the reference holds comfortably (int indexing and 144 B/cell stop it near 15000^2; "
+                                "32768^2 is out of its reach); MLUPS is per cell, so the figure compares directly with `value`")
+            ref_cuda["speedup_of_value"] = mlups / ref_cuda["mlups"]
+        configs = [run_config(name, peak) for name in ("c1", "c2", "c3", "c3_lagged", "c5")]
 
     if rank == 0:
         line = {"metric": "MLUPS", "value": mlups, "unit": "MLUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -277,14 +393,14 @@ def main():
                 "config": {"workload": f"taylor_green_d2q9_{args.collision.lower()}_{nx}x{ny}_periodic_yslab", "nx": nx, "ny": ny,
                            "collision": args.collision, "rows_per_gpu": eng.ny_local, "quirks": "reference-compatible", "slab_coupling": solver.mode,
                            "l2_policy": f"populations per GPU {36.0 * nloc / 1e9:.1f} GB >> 126 MB L2 (no flush needed)"},
-                "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
+                "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "check": check,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": traffic, "traffic_source": "ncu dram bytes per launch, mean of the odd/even phase captures (profiles/r01_ncu_bench_kernel.md)",
+                             "traffic": traffic,
+                             "traffic_source": "citation: ncu --set full of this command at N = 1, dram__bytes_read.sum + dram__bytes_write.sum per launch, mean of the odd / even phase captures (profiles/r01_ncu_bench_kernel.md), scaled by rows per rank; not re-measured by this run",
                              "peak_source": peak_src, "kernel": "lbm::step_vec_kernel<BGK, odd|even> (fused pull + collide + push, 4 cells/thread)",
                              "algorithmic_bytes_per_launch": BYTES_PER_UPDATE * nloc, "kernel_ms": kern_ms},
-                "cpu_baseline": cpu}
+                "cpu_baseline": cpu, "reference_cuda": ref_cuda, "configs": configs}
         print(json.dumps(line), flush=True)
-    eng.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -8,12 +8,14 @@
 // <dir with scenarios/...> is the reference's src/ (its scenario files compile unchanged) or examples/ (this repo's own).
 // Any other scenario:  -DSCENARIO_HEADER='"my/scenario.cuh"' -DSCENARIO_TYPE=MyScenario -DNX=.. -DNY=..
 //
-//   ./tg [--steps N] [--save-int K] [--vtk] [--dump] [--fast] [--load-ckpt FILE] [--save-ckpt FILE]
+//   ./tg [--steps N] [--save-int K] [--warmup W] [--vtk] [--dump] [--fast] [--load-ckpt FILE] [--save-ckpt FILE]
+//     --warmup W    W untimed steps first (module load, CUDA-graph capture); --steps counts the timed steps that follow
 //     --save-int K  every K steps: update_macroscopics + compute_error (and --vtk: save_vtk, --dump: save_macroscopics)
 //     --fast        no per-step host calls between save points (LBM::run), the throughput mode
 //     --load-ckpt F continue from a checkpoint written by --save-ckpt (same binary); --steps counts the steps still to run
 //     --save-ckpt F write the population state after the last step
 #include <stdio.h>
+#include <chrono>
 #include <cstring>
 #include <iostream>
 #include "core/lbm.cuh"
@@ -41,12 +43,13 @@ using Scenario = FlowPastCylinderScenario;
 #endif
 
 int main(int argc, char** argv) {
-    int total_timesteps = 1000, save_int = 100;
+    int total_timesteps = 1000, save_int = 100, warmup = 0;
     bool vtk = false, dump = false, fast = false;
     const char *load_ckpt = nullptr, *save_ckpt = nullptr;
     for (int i = 1; i < argc; i++) {
         if (!strcmp(argv[i], "--steps") && i + 1 < argc) total_timesteps = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--save-int") && i + 1 < argc) save_int = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "--warmup") && i + 1 < argc) warmup = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--vtk")) vtk = true;
         else if (!strcmp(argv[i], "--dump")) dump = true;
         else if (!strcmp(argv[i], "--fast")) fast = true;
@@ -70,6 +73,10 @@ int main(int argc, char** argv) {
         lbm.load_checkpoint<Scenario>(load_ckpt);
         printf("restarted from %s at step %d\n", load_ckpt, lbm.timestep);
     }
+    if (warmup > 0) {
+        lbm.run<Scenario>(warmup);
+        lbm.synchronize();
+    }
     const int first_step = lbm.timestep;
 
     cudaEvent_t start, stop;
@@ -79,6 +86,7 @@ int main(int argc, char** argv) {
     int t = 0;
     while (t < total_timesteps) {
         const int chunk = std::min(save_int, total_timesteps - t);
+        const auto wall0 = std::chrono::steady_clock::now();
         cudaEventRecord(start);
         if (fast) {
             lbm.run<Scenario>(chunk);
@@ -98,10 +106,12 @@ int main(int argc, char** argv) {
         }
         t += chunk;
         lbm.finish_step();                  // the last step of the chunk also stores rho and u (+12 B/node on that step only)
+        if (lbm.num_slabs() > 1) lbm.synchronize();        // several GPUs (LBM_B200_GPUS): events on this device's stream do not see the others
         cudaEventRecord(stop);
         cudaEventSynchronize(stop);
         float ms = 0.0f;
         cudaEventElapsedTime(&ms, start, stop);
+        if (lbm.num_slabs() > 1) ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - wall0).count();
         gpu_ms += ms;
         lbm.update_macroscopics();          // device -> host copy of rho, u: outside the timed region, as in the reference's save path
         if (vtk) lbm.save_vtk(t);
@@ -123,8 +133,8 @@ int main(int argc, char** argv) {
     double sum_rho = 0.0, sum_u2 = 0.0;
     for (size_t i = 0; i < lbm.h_rho.size(); i++) sum_rho += lbm.h_rho[i];
     for (size_t i = 0; i < lbm.h_u.size(); i++) sum_u2 += (double)lbm.h_u[i] * lbm.h_u[i];
-    printf("SHIM_RESULT scenario=%s nx=%d ny=%d steps=%d ms_per_step=%.6f mlups=%.3f error_pct=%.6f mass_per_node=%.9f mean_rho=%.9f sum_u2=%.9e\n",
-           Scenario::name(), NX, NY, total_timesteps, gpu_ms / total_timesteps,
+    printf("SHIM_RESULT scenario=%s gpus=%d nx=%d ny=%d steps=%d ms_per_step=%.6f mlups=%.3f error_pct=%.6f mass_per_node=%.9f mean_rho=%.9f sum_u2=%.9e\n",
+           Scenario::name(), lbm.num_slabs(), NX, NY, total_timesteps, gpu_ms / total_timesteps,
            lbm_b200_mlups((long long)NX * NY, total_timesteps, gpu_ms * 1e-3), last_error, mass / ((double)NX * NY),
            sum_rho / ((double)NX * NY), sum_u2);
     return 0;

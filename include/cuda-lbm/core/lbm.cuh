@@ -22,15 +22,19 @@
 #define LBM_H
 
 #include <cmath>
+#include <condition_variable>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
 #include <filesystem>
 #include <fstream>
+#include <functional>
 #include <iomanip>
 #include <iostream>
+#include <mutex>
 #include <sstream>
 #include <string>
+#include <thread>
 #include <type_traits>
 #include <vector>
 
@@ -67,17 +71,18 @@ template <typename S> struct periodic_x_of<S, std::void_t<decltype(S::periodic_x
 template <typename S, typename = void> struct periodic_y_of { static constexpr bool value = lbm_b200_periodic_y_default; };
 template <typename S> struct periodic_y_of<S, std::void_t<decltype(S::periodic_y)>> { static constexpr bool value = S::periodic_y; };
 
-// Init functor over the whole grid, one node per thread: init_kernel of src/core/init/init.cuh:29-43 without the population part
+// Init functor over a slab's rows, one node per thread: init_kernel of src/core/init/init.cuh:29-43 without the population part.
+// The functor indexes whole-grid arrays with the global node; the base pointers are shifted so that node `first` is element 0.
 template <typename Init>
-__global__ void init_functor_kernel(Init init, float* rho, float* u, float* force, int n) {
+__global__ void slab_init_functor_kernel(Init init, float* rho, float* u, float* force, long long first, long long n) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) init(rho, u, force, (int)i);
+    if (i < n) init(rho, u, force, (int)(first + i));
 }
 // reset_forces_kernel of src/core/macroscopics/macroscopics.cuh:13-27
 template <typename Init>
-__global__ void force_functor_kernel(Init init, float* rho, float* u, float* force, int n) {
+__global__ void slab_force_functor_kernel(Init init, float* rho, float* u, float* force, long long first, long long n) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) init.apply_forces(rho, u, force, (int)i);
+    if (i < n) init.apply_forces(rho, u, force, (int)(first + i));
 }
 // Boundary functor over the whole grid (setup_boundary_flags, src/core/boundaries/boundaries.cuh:170-197, runs it on the host)
 template <typename Boundary>
@@ -96,13 +101,13 @@ static __global__ void force_uniform_kernel(const float2* force, int n, int* dif
     if (a.x != b.x || a.y != b.y) *differs = 1;
 }
 
-// Validation functor over the whole grid: (x, y) -> analytic velocity (taylorGreenFunctors.cuh:66-81, poiseuilleFunctors.cuh:72-75)
+// Validation functor over a slab's rows: (x, y) -> analytic velocity (taylorGreenFunctors.cuh:66-81, poiseuilleFunctors.cuh:72-75)
 template <typename Validation>
-__global__ void validation_functor_kernel(Validation v, float2* u_ref, int nx, int ny) {
+__global__ void validation_functor_kernel(Validation v, float2* u_ref, int nx, int y0, int nyl) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (long long)nx * ny) return;
+    if (i >= (long long)nx * nyl) return;
     float ux = 0.0f, uy = 0.0f;
-    v((int)(i % nx), (int)(i / nx), ux, uy);
+    v((int)(i % nx), y0 + (int)(i / nx), ux, uy);
     u_ref[i] = make_float2(ux, uy);
 }
 
@@ -118,26 +123,120 @@ inline int env_int(const char* name, int fallback) {
 
 }  // namespace lbm_b200_shim
 
+namespace lbm_b200_shim {
+
+// One host thread per slab when the domain is split over several GPUs: every slab's calls are enqueued from its own thread,
+// so no slab's launch queue can fill up (and block the host) while another slab — whose step counter it waits for on the
+// device — has not been enqueued yet.  A single slab runs inline on the caller's thread.
+class SlabThreads {
+    std::vector<std::thread> th;
+    std::mutex m;
+    std::condition_variable go, done;
+    std::function<void(int)> job;
+    unsigned long generation = 0;
+    int pending = 0;
+    bool quit = false;
+
+    void loop(int g, int device) {
+        cudaSetDevice(device);
+        unsigned long seen = 0;
+        for (;;) {
+            std::function<void(int)> f;
+            {
+                std::unique_lock<std::mutex> lk(m);
+                go.wait(lk, [&] { return quit || generation != seen; });
+                if (quit) return;
+                seen = generation;
+                f = job;
+            }
+            f(g);
+            {
+                std::lock_guard<std::mutex> lk(m);
+                if (--pending == 0) done.notify_all();
+            }
+        }
+    }
+
+public:
+    void start(const std::vector<int>& devices) {
+        stop();
+        quit = false;
+        if (devices.size() > 1)
+            for (int g = 0; g < (int)devices.size(); g++) th.emplace_back([this, g, d = devices[g]] { loop(g, d); });
+    }
+    template <typename F>
+    void run(int n, F&& f) {
+        if (th.empty()) { for (int g = 0; g < n; g++) f(g); return; }
+        {
+            std::lock_guard<std::mutex> lk(m);
+            job = std::function<void(int)>(f);
+            pending = (int)th.size();
+            generation++;
+        }
+        go.notify_all();
+        std::unique_lock<std::mutex> lk(m);
+        done.wait(lk, [&] { return pending == 0; });
+    }
+    void stop() {
+        { std::lock_guard<std::mutex> lk(m); quit = true; }
+        go.notify_all();
+        for (auto& t : th) t.join();
+        th.clear();
+    }
+    ~SlabThreads() { stop(); }
+};
+
+// scenarios whose body force changes in time declare `static constexpr bool time_dependent_forces = true;` (detected, never required):
+// reset_forces<Scenario>() then re-evaluates Init::apply_forces every step, as the reference does for every scenario
+// (src/core/macroscopics/macroscopics.cuh:13-48); without the member the force is evaluated once, at init()
+template <typename S, typename = void> struct has_time_dependent_forces : std::false_type {};
+template <typename S> struct has_time_dependent_forces<S, std::void_t<decltype(S::time_dependent_forces)>> : std::bool_constant<S::time_dependent_forces> {};
+
+}  // namespace lbm_b200_shim
+
 template <int dim>
 class LBM {
     static_assert(dim == 2, "the B200 engine covers the reference's D2Q9 path (LBM<2>)");
 
 private:
-    lbm_handle* h = nullptr;
+    // The domain is one slab on the current device (the reference's configuration) or, with LBM_B200_GPUS=N in the environment
+    // ("all" = every visible device), N y-slabs on N GPUs of the box: one engine handle, one host thread and one stream per slab,
+    // all slabs peer-mapped (halo rows, IBM node states and the adapter sums travel over NVLink inside the kernels).
+    struct Slab { lbm_handle* h = nullptr; int device = 0, y0 = 0, nyl = 0; float* d_force = nullptr; };
+    std::vector<Slab> slabs;
+    lbm_b200_shim::SlabThreads workers;
+    lbm_handle* h = nullptr;             // slabs[0].h
+    int home_device = 0;
     bool step_pending = false;           // a step has been described (collide) but not enqueued yet
     std::vector<IBMBody> bodies;         // owned from allocate() on, released in free()
+    void (LBM::*force_refresh)() = nullptr;      // set by reset_forces<S>() of a scenario with time-dependent forces
+
+    template <typename F>
+    void each_slab(F&& f) {
+        workers.run((int)slabs.size(), [&](int g) {
+            if (slabs.size() > 1) cudaSetDevice(slabs[g].device);
+            f(slabs[g], g);
+        });
+    }
 
     void flush(bool want_macroscopics) {
         if (!step_pending) return;
-        if (want_macroscopics) LBM_B200_CALL(lbm_step_with_macroscopics(h, 1));
-        else LBM_B200_CALL(lbm_step(h, 1));
+        if (force_refresh) { (this->*force_refresh)(); want_macroscopics = true; }      // the next evaluation reads this step's rho / u
+        each_slab([&](Slab& s, int) {
+            if (want_macroscopics) LBM_B200_CALL(lbm_step_with_macroscopics(s.h, 1));
+            else LBM_B200_CALL(lbm_step(s.h, 1));
+        });
         step_pending = false;
     }
 
     template <typename Scenario>
     void send_consts() {
         const float nu = Scenario::viscosity;
-        checkCudaErrors(cudaMemcpyToSymbol(vis, &nu, sizeof(float)));
+        for (const Slab& s : slabs) {
+            checkCudaErrors(cudaSetDevice(s.device));
+            checkCudaErrors(cudaMemcpyToSymbol(vis, &nu, sizeof(float)));
+        }
+        checkCudaErrors(cudaSetDevice(home_device));
     }
 
     template <typename BoundaryFunctor>
@@ -153,35 +252,69 @@ private:
         if (any) {      // an all-FLUID scenario (Taylor-Green) needs no flag plane at all
             std::vector<int32_t> flags((size_t)n);
             checkCudaErrors(cudaMemcpy(flags.data(), d_flags, n * sizeof(int), cudaMemcpyDeviceToHost));
-            LBM_B200_CALL(lbm_set_flags(h, flags.data()));
+            for (const Slab& s : slabs) LBM_B200_CALL(lbm_set_flags(s.h, flags.data()));       // every slab picks its rows
+            checkCudaErrors(cudaSetDevice(home_device));
         }
         checkCudaErrors(cudaFree(d_flags));
         checkCudaErrors(cudaFree(d_any));
     }
 
-    // Init::apply_forces for every node -> uniform body force (two kernel constants) or a per-node force plane
+    // The functors index whole-grid arrays with the GLOBAL node (rho[node], u[2*node+c] / u[get_vec_index(node, c)]): a
+    // slab hands them base pointers shifted by its first node, so that the writes land in its own rows' storage.
     template <typename Init>
-    void upload_forces(Init init, float* d_rho, float* d_u, float* d_force, bool evaluate) {
-        const int n = NX * NY;
-        if (evaluate) {
-            lbm_b200_shim::force_functor_kernel<<<(n + 255) / 256, 256>>>(init, d_rho, d_u, d_force, n);
-            checkCudaErrors(cudaGetLastError());
+    void run_force_functor(Init init, const Slab& s, const float* d_rho_local, const float* d_u_local) {
+        const long long n = (long long)s.nyl * NX, first = (long long)s.y0 * NX;
+        lbm_b200_shim::slab_force_functor_kernel<<<(unsigned)((n + 255) / 256), 256>>>(init, const_cast<float*>(d_rho_local) - first,
+                                                                                    const_cast<float*>(d_u_local) - 2 * first, s.d_force - 2 * first, first, n);
+        checkCudaErrors(cudaGetLastError());
+    }
+
+    // Init::apply_forces for every node -> one uniform body force (two kernel constants) or a per-node force plane
+    template <typename Init>
+    void upload_forces(Init init, const std::vector<float*>& d_rho, const std::vector<float*>& d_u) {
+        std::vector<int> differs(slabs.size(), 0);
+        std::vector<float> f0(2 * slabs.size(), 0.0f);
+        for (size_t g = 0; g < slabs.size(); g++) {
+            const Slab& s = slabs[g];
+            checkCudaErrors(cudaSetDevice(s.device));
+            const int n = s.nyl * NX;
+            run_force_functor(init, s, d_rho[g], d_u[g]);
+            int* d_differs = nullptr;
+            checkCudaErrors(cudaMalloc(&d_differs, sizeof(int)));
+            checkCudaErrors(cudaMemset(d_differs, 0, sizeof(int)));
+            lbm_b200_shim::force_uniform_kernel<<<(n + 255) / 256, 256>>>(reinterpret_cast<const float2*>(s.d_force), n, d_differs);
+            checkCudaErrors(cudaMemcpy(&differs[g], d_differs, sizeof(int), cudaMemcpyDeviceToHost));
+            checkCudaErrors(cudaMemcpy(&f0[2 * g], s.d_force, 2 * sizeof(float), cudaMemcpyDeviceToHost));
+            checkCudaErrors(cudaFree(d_differs));
         }
-        int* d_differs = nullptr;
-        int differs = 0;
-        checkCudaErrors(cudaMalloc(&d_differs, sizeof(int)));
-        checkCudaErrors(cudaMemset(d_differs, 0, sizeof(int)));
-        lbm_b200_shim::force_uniform_kernel<<<(n + 255) / 256, 256>>>(reinterpret_cast<const float2*>(d_force), n, d_differs);
-        checkCudaErrors(cudaMemcpy(&differs, d_differs, sizeof(int), cudaMemcpyDeviceToHost));
-        checkCudaErrors(cudaFree(d_differs));
-        if (differs) {
-            LBM_B200_CALL(lbm_set_force_field_device(h, d_force));
-        } else {
-            float f0[2];
-            checkCudaErrors(cudaMemcpy(f0, d_force, sizeof(f0), cudaMemcpyDeviceToHost));
-            LBM_B200_CALL(lbm_set_force_field(h, nullptr));
-            LBM_B200_CALL(lbm_set_body_force(h, f0[0], f0[1]));
+        bool uniform = true;
+        for (size_t g = 0; g < slabs.size(); g++) uniform = uniform && !differs[g] && f0[2 * g] == f0[0] && f0[2 * g + 1] == f0[1];
+        for (const Slab& s : slabs) {
+            checkCudaErrors(cudaSetDevice(s.device));
+            if (uniform) {
+                LBM_B200_CALL(lbm_set_force_field(s.h, nullptr));
+                LBM_B200_CALL(lbm_set_body_force(s.h, f0[0], f0[1]));
+            } else {
+                LBM_B200_CALL(lbm_set_force_field_device(s.h, s.d_force));
+            }
         }
+        checkCudaErrors(cudaSetDevice(home_device));
+    }
+
+    // reset_forces<Scenario>() of a scenario with time-dependent forces: Init::apply_forces with Scenario::t of the step being
+    // described and the macroscopic fields of the last completed step (the reference hands it the uncorrected moments of the
+    // step in flight, which a fused step does not materialise; identical for forces that depend on position and time only)
+    template <typename Scenario>
+    void eval_forces_now() {
+        auto init = Scenario::init();
+        each_slab([&](Slab& s, int) {
+            LBM_B200_CALL(lbm_recover_macroscopics(s.h));
+            const float *r = nullptr, *u = nullptr;
+            LBM_B200_CALL(lbm_get_macroscopics_device(s.h, &r, &u));
+            run_force_functor(init, s, r, u);
+            checkCudaErrors(cudaDeviceSynchronize());
+            LBM_B200_CALL(lbm_set_force_field_device(s.h, s.d_force));
+        });
     }
 
 public:
@@ -193,6 +326,8 @@ public:
     LBM(const LBM&) = delete;
     LBM& operator=(const LBM&) = delete;
 
+    int num_slabs() const { return (int)slabs.size(); }
+
     // LBM::allocate<Scenario>() — src/core/lbm.cuh:92-125
     template <typename Scenario>
     void allocate() {
@@ -200,40 +335,74 @@ public:
         h_rho.resize((size_t)NX * NY);
         h_u.resize((size_t)NX * NY * dimensions);
 
-        lbm_config cfg;
-        LBM_B200_CALL(lbm_default_config(&cfg));
-        cfg.nx = NX;
-        cfg.ny = NY;
-        cfg.periodic_x = lbm_b200_shim::periodic_x_of<Scenario>::value;
-        cfg.periodic_y = lbm_b200_shim::periodic_y_of<Scenario>::value;
-        cfg.collision = Scenario::CollisionOp::lbm_b200_op;
-        cfg.viscosity = Scenario::viscosity;
-        for (int i = 0; i < quadratures; i++) cfg.S[i] = Scenario::S[i];
-        cfg.u_max = Scenario::u_max;
-        // LBM_QK_REFERENCE reproduces the reference's arithmetic including its defects; 0 repairs them
-        cfg.quirks = lbm_b200_shim::env_int("LBM_B200_QUIRKS", LBM_QK_REFERENCE);
-        cfg.adapter_mode = lbm_b200_shim::env_int("LBM_B200_ADAPTER", LBM_ADAPTER_EXACT);
-        int dev = 0;
-        checkCudaErrors(cudaGetDevice(&dev));
-        cfg.device = dev;
-        LBM_B200_CALL(lbm_create(&cfg, &h));
-        LBM_B200_CALL(lbm_set_stream(h, (void*)cudaStreamLegacy));
+        checkCudaErrors(cudaGetDevice(&home_device));
+        int ndev = 1;
+        checkCudaErrors(cudaGetDeviceCount(&ndev));
+        int G = 1;
+        if (const char* v = std::getenv("LBM_B200_GPUS")) G = (v[0] == 'a' || v[0] == 'A') ? ndev : std::max(1, std::atoi(v));
+        if (G > NY / 2) G = std::max(1, NY / 2);
+        slabs.assign((size_t)G, Slab());
+        std::vector<int> devices;
+        for (int g = 0; g < G; g++) {
+            lbm_config cfg;
+            LBM_B200_CALL(lbm_default_config(&cfg));
+            cfg.nx = NX;
+            cfg.ny = NY;
+            cfg.periodic_x = lbm_b200_shim::periodic_x_of<Scenario>::value;
+            cfg.periodic_y = lbm_b200_shim::periodic_y_of<Scenario>::value;
+            cfg.collision = Scenario::CollisionOp::lbm_b200_op;
+            cfg.viscosity = Scenario::viscosity;
+            for (int i = 0; i < quadratures; i++) cfg.S[i] = Scenario::S[i];
+            cfg.u_max = Scenario::u_max;
+            // LBM_QK_REFERENCE reproduces the reference's arithmetic including its defects; 0 repairs them
+            cfg.quirks = lbm_b200_shim::env_int("LBM_B200_QUIRKS", LBM_QK_REFERENCE);
+            cfg.adapter_mode = lbm_b200_shim::env_int("LBM_B200_ADAPTER", LBM_ADAPTER_EXACT);
+            cfg.device = G == 1 ? home_device : g % ndev;       // more slabs than devices: they share (diagnosis / tests on a one-GPU box)
+            cfg.rank = g;
+            cfg.world = G;
+            Slab& s = slabs[(size_t)g];
+            LBM_B200_CALL(lbm_create(&cfg, &s.h));
+            lbm_info_t inf;
+            LBM_B200_CALL(lbm_info(s.h, &inf));
+            s.device = cfg.device; s.y0 = inf.y0; s.nyl = inf.ny_local;
+            devices.push_back(s.device);
+        }
+        h = slabs[0].h;
+        if (G == 1) {
+            LBM_B200_CALL(lbm_set_stream(h, (void*)cudaStreamLegacy));      // cudaEventRecord(…, 0) pairs in a reference-style driver time the work
+        } else {
+            std::vector<unsigned char> descs((size_t)G * LBM_PEER_DESC_BYTES);
+            for (int g = 0; g < G; g++) LBM_B200_CALL(lbm_peer_export(slabs[(size_t)g].h, descs.data() + (size_t)g * LBM_PEER_DESC_BYTES));
+            for (int g = 0; g < G; g++) LBM_B200_CALL(lbm_peer_attach_all(slabs[(size_t)g].h, descs.data(), G));
+            std::cout << "[LBM]: " << G << " y-slabs on " << std::min(G, ndev) << " GPU(s), peer-mapped\n";
+        }
+        checkCudaErrors(cudaSetDevice(home_device));
+        workers.start(devices);
 
         Scenario::add_bodies();
         for (const IBMBody& b : Scenario::IBM_bodies) {
-            LBM_B200_CALL(lbm_add_body(h, b.points, b.num_points));
-            // IBMBody::velocities: dead data in the reference (IBM_impl.cuh:15, A-D9) and here under LBM_QK_D9_IBM_ZERO_TARGET
-            // (part of LBM_QK_REFERENCE); with that bit cleared (LBM_B200_QUIRKS) the markers force the fluid towards them
-            if (b.velocities && b.num_points > 0) LBM_B200_CALL(lbm_set_body_velocities(h, (int)bodies.size(), b.velocities));
+            for (const Slab& s : slabs) {       // every slab is given every body; it works on those that reach into its rows
+                LBM_B200_CALL(lbm_add_body(s.h, b.points, b.num_points));
+                // IBMBody::velocities: dead data in the reference (IBM_impl.cuh:15, A-D9) and here under LBM_QK_D9_IBM_ZERO_TARGET
+                // (part of LBM_QK_REFERENCE); with that bit cleared (LBM_B200_QUIRKS) the markers force the fluid towards them
+                if (b.velocities && b.num_points > 0) LBM_B200_CALL(lbm_set_body_velocities(s.h, (int)bodies.size(), b.velocities));
+            }
             bodies.push_back(b);
         }
+        checkCudaErrors(cudaSetDevice(home_device));
     }
 
     void free() {
-        if (!h) return;
+        if (slabs.empty()) return;
         std::cout << "[LBM]: Freeing\n";
         step_pending = false;
-        LBM_B200_CALL(lbm_destroy(h));
+        workers.stop();
+        for (Slab& s : slabs) {
+            if (s.d_force) { cudaSetDevice(s.device); cudaFree(s.d_force); }
+            LBM_B200_CALL(lbm_destroy(s.h));
+        }
+        cudaSetDevice(home_device);
+        slabs.clear();
         h = nullptr;
         for (IBMBody& b : bodies) h_ibm_free(b);
         bodies.clear();
@@ -249,30 +418,42 @@ public:
         auto boundary_func = Scenario::boundary();
         send_consts<Scenario>();
 
-        const int n = NX * NY;
-        float *d_rho = nullptr, *d_u = nullptr, *d_force = nullptr;
-        checkCudaErrors(cudaMalloc(&d_rho, (size_t)n * sizeof(float)));
-        checkCudaErrors(cudaMalloc(&d_u, (size_t)n * 2 * sizeof(float)));
-        checkCudaErrors(cudaMalloc(&d_force, (size_t)n * 2 * sizeof(float)));
-        // entries a functor leaves unwritten are zero here (the reference reads uninitialised memory, Appendix A-D13)
-        checkCudaErrors(cudaMemset(d_rho, 0, (size_t)n * sizeof(float)));
-        checkCudaErrors(cudaMemset(d_u, 0, (size_t)n * 2 * sizeof(float)));
-        checkCudaErrors(cudaMemset(d_force, 0, (size_t)n * 2 * sizeof(float)));
-        lbm_b200_shim::init_functor_kernel<<<(n + 255) / 256, 256>>>(init, d_rho, d_u, d_force, n);
-        checkCudaErrors(cudaGetLastError());
-        checkCudaErrors(cudaDeviceSynchronize());
+        // the Init functor on every slab's device over that slab's rows
+        std::vector<float*> d_rho(slabs.size(), nullptr), d_u(slabs.size(), nullptr);
+        for (size_t g = 0; g < slabs.size(); g++) {
+            Slab& s = slabs[g];
+            checkCudaErrors(cudaSetDevice(s.device));
+            const long long n = (long long)s.nyl * NX, first = (long long)s.y0 * NX;
+            checkCudaErrors(cudaMalloc(&d_rho[g], (size_t)n * sizeof(float)));
+            checkCudaErrors(cudaMalloc(&d_u[g], (size_t)n * 2 * sizeof(float)));
+            if (!s.d_force) checkCudaErrors(cudaMalloc(&s.d_force, (size_t)n * 2 * sizeof(float)));
+            // entries a functor leaves unwritten are zero here (the reference reads uninitialised memory, Appendix A-D13)
+            checkCudaErrors(cudaMemset(d_rho[g], 0, (size_t)n * sizeof(float)));
+            checkCudaErrors(cudaMemset(d_u[g], 0, (size_t)n * 2 * sizeof(float)));
+            checkCudaErrors(cudaMemset(s.d_force, 0, (size_t)n * 2 * sizeof(float)));
+            lbm_b200_shim::slab_init_functor_kernel<<<(unsigned)((n + 255) / 256), 256>>>(init, d_rho[g] - first, d_u[g] - 2 * first, s.d_force - 2 * first, first, n);
+            checkCudaErrors(cudaGetLastError());
+            checkCudaErrors(cudaDeviceSynchronize());
+        }
+        checkCudaErrors(cudaSetDevice(home_device));
 
         setup_boundary_flags(boundary_func);
-        upload_forces(init, d_rho, d_u, d_force, true);     // what reset_forces<Scenario>() computes every step in the reference
-        LBM_B200_CALL(lbm_init_fields_device(h, d_rho, d_u));
-        LBM_B200_CALL(lbm_sync(h));
-        checkCudaErrors(cudaFree(d_rho));
-        checkCudaErrors(cudaFree(d_u));
-        checkCudaErrors(cudaFree(d_force));
+        upload_forces(init, d_rho, d_u);            // what reset_forces<Scenario>() computes every step in the reference
+        for (size_t g = 0; g < slabs.size(); g++) {
+            const Slab& s = slabs[g];
+            checkCudaErrors(cudaSetDevice(s.device));
+            LBM_B200_CALL(lbm_init_fields_device(s.h, d_rho[g], d_u[g]));
+            LBM_B200_CALL(lbm_sync(s.h));
+            checkCudaErrors(cudaFree(d_rho[g]));
+            checkCudaErrors(cudaFree(d_u[g]));
+            if (!lbm_b200_shim::has_time_dependent_forces<Scenario>::value) { checkCudaErrors(cudaFree(slabs[g].d_force)); slabs[g].d_force = nullptr; }
+        }
+        checkCudaErrors(cudaSetDevice(home_device));
         timestep = 0;
         update_ts = 0;
         step_pending = false;
-        printf("[init_kernel]: Threads executed: %d\n", n);
+        force_refresh = nullptr;
+        printf("[init_kernel]: Threads executed: %d\n", NX * NY);
     }
 
     template <typename Scenario>
@@ -287,8 +468,13 @@ public:
     void swap_buffers() {}
     template <typename Scenario> void apply_boundaries() {}
     void uncorrected_macroscopics() {}
-    // Init::apply_forces was evaluated in init(); a scenario whose force changes in time calls refresh_forces<S>() instead
-    template <typename Scenario> void reset_forces() {}
+    // Init::apply_forces was evaluated in init().  A scenario that declares `static constexpr bool time_dependent_forces = true;`
+    // gets the reference's behaviour — re-evaluated for every step (src/core/macroscopics/macroscopics.cuh:13-48) — at the price
+    // of a force plane and the general (scalar) kernel path.
+    template <typename Scenario>
+    void reset_forces() {
+        if constexpr (lbm_b200_shim::has_time_dependent_forces<Scenario>::value) force_refresh = &LBM::template eval_forces_now<Scenario>;
+    }
     void ibm_step() {}
     void correct_macroscopics() {}
     void compute_equilibrium() {}
@@ -305,59 +491,58 @@ public:
     void run(int n) {
         if (n <= 0) return;
         flush(false);
-        LBM_B200_CALL(lbm_step(h, n - 1));
+        if constexpr (lbm_b200_shim::has_time_dependent_forces<Scenario>::value) {
+            for (int i = 0; i < n; i++) {           // the force changes between steps: one at a time
+                increase_ts<Scenario>();
+                reset_forces<Scenario>();
+                collide<typename Scenario::CollisionOp>();
+            }
+            return;
+        }
+        each_slab([&](Slab& s, int) { LBM_B200_CALL(lbm_step(s.h, n - 1)); });
         timestep += n;
         Scenario::update_ts(timestep);
         step_pending = true;
     }
 
     // extension: enqueue the step described so far now (instead of at the next increase_ts), keeping its rho / u for a
-    // following update_macroscopics() — lets a driver bracket exactly the stepping work with CUDA events
+    // following update_macroscopics() — lets a driver bracket exactly the stepping work with CUDA events (one slab) or with
+    // synchronize() and a wall clock (several slabs)
     void finish_step(bool keep_macroscopics = true) { flush(keep_macroscopics); }
 
-    // extension: re-evaluate Init::apply_forces with the macroscopic fields of the last update_macroscopics()
+    // extension: re-evaluate Init::apply_forces now (with the macroscopic fields of the last completed step)
     template <typename Scenario>
     void refresh_forces() {
-        flush(false);
-        const int n = NX * NY;
-        float *d_rho = nullptr, *d_u = nullptr, *d_force = nullptr;
-        checkCudaErrors(cudaMalloc(&d_rho, (size_t)n * sizeof(float)));
-        checkCudaErrors(cudaMalloc(&d_u, (size_t)n * 2 * sizeof(float)));
-        checkCudaErrors(cudaMalloc(&d_force, (size_t)n * 2 * sizeof(float)));
-        checkCudaErrors(cudaMemcpy(d_rho, h_rho.data(), (size_t)n * sizeof(float), cudaMemcpyHostToDevice));
-        checkCudaErrors(cudaMemcpy(d_u, h_u.data(), (size_t)n * 2 * sizeof(float), cudaMemcpyHostToDevice));
-        checkCudaErrors(cudaMemset(d_force, 0, (size_t)n * 2 * sizeof(float)));
-        upload_forces(Scenario::init(), d_rho, d_u, d_force, true);
-        checkCudaErrors(cudaFree(d_rho));
-        checkCudaErrors(cudaFree(d_u));
-        checkCudaErrors(cudaFree(d_force));
+        flush(true);
+        for (Slab& s : slabs)
+            if (!s.d_force) { checkCudaErrors(cudaSetDevice(s.device)); checkCudaErrors(cudaMalloc(&s.d_force, (size_t)s.nyl * NX * 2 * sizeof(float))); }
+        checkCudaErrors(cudaSetDevice(home_device));
+        std::vector<float*> d_rho, d_u;
+        for (Slab& s : slabs) {
+            LBM_B200_CALL(lbm_recover_macroscopics(s.h));
+            const float *r = nullptr, *u = nullptr;
+            LBM_B200_CALL(lbm_get_macroscopics_device(s.h, &r, &u));
+            LBM_B200_CALL(lbm_sync(s.h));
+            d_rho.push_back(const_cast<float*>(r)); d_u.push_back(const_cast<float*>(u));
+        }
+        upload_forces(Scenario::init(), d_rho, d_u);
     }
 
     // LBM::update_macroscopics() — src/core/lbm.cuh:148-154
     void update_macroscopics() {
         flush(true);        // no-op after finish_step(): the macroscopics of the current step are already on the device
-        // the step was closed without them (increase_ts() of the next step came first): rebuilt from its populations, so that —
-        // as in the reference, whose d_rho / d_u are always current — this call is legal at any point of the driver loop
-        LBM_B200_CALL(lbm_recover_macroscopics(h));
         update_ts = timestep;
-        LBM_B200_CALL(lbm_get_macroscopics(h, h_rho.data(), h_u.data()));
+        each_slab([&](Slab& s, int) {
+            // the step was closed without them (increase_ts() of the next step came first): rebuilt from its populations, so that —
+            // as in the reference, whose d_rho / d_u are always current — this call is legal at any point of the driver loop
+            LBM_B200_CALL(lbm_recover_macroscopics(s.h));
+            LBM_B200_CALL(lbm_get_macroscopics(s.h, h_rho.data() + (size_t)s.y0 * NX, h_u.data() + (size_t)s.y0 * NX * 2));
+        });
     }
 
-    // device views of rho[node] and u[node*2+c], valid until the next step (d_rho / d_u of the reference)
-    float* get_rho() {
-        flush(true);
-        LBM_B200_CALL(lbm_recover_macroscopics(h));
-        const float *r = nullptr, *u = nullptr;
-        LBM_B200_CALL(lbm_get_macroscopics_device(h, &r, &u));
-        return const_cast<float*>(r);
-    }
-    float* get_u() {
-        flush(true);
-        LBM_B200_CALL(lbm_recover_macroscopics(h));
-        const float *r = nullptr, *u = nullptr;
-        LBM_B200_CALL(lbm_get_macroscopics_device(h, &r, &u));
-        return const_cast<float*>(u);
-    }
+    // device views of rho[node] and u[node*2+c], valid until the next step (d_rho / d_u of the reference); one slab only
+    float* get_rho() { return const_cast<float*>(device_macroscopics(0)); }
+    float* get_u() { return const_cast<float*>(device_macroscopics(1)); }
 
     // LBM::compute_error<Scenario>() — src/core/lbm.cuh:163-171
     template <typename Scenario>
@@ -372,32 +557,39 @@ public:
 
     // extension: the relative L2 velocity error in percent against Scenario::validation() (the metric of
     // taylorGreenScenario.cuh:59-88) with the functor evaluated and both sums taken on the device (fp64, fixed order):
-    // nothing but two doubles crosses PCIe, where compute_error<S>() moves 12 B/node to the host first
+    // nothing but two doubles per slab crosses PCIe, where compute_error<S>() moves 12 B/node to the host first
     template <typename Scenario>
     float l2_error_device() {
         flush(true);
-        LBM_B200_CALL(lbm_recover_macroscopics(h));
-        const long long n = (long long)NX * NY;
-        float2* d_ref = nullptr;
-        checkCudaErrors(cudaMalloc(&d_ref, (size_t)n * sizeof(float2)));
-        lbm_b200_shim::validation_functor_kernel<<<(unsigned)((n + 255) / 256), 256>>>(Scenario::validation(), d_ref, NX, NY);
-        checkCudaErrors(cudaGetLastError());
-        double sums[2] = {0.0, 0.0};
-        LBM_B200_CALL(lbm_velocity_error_sums(h, reinterpret_cast<const float*>(d_ref), sums));
-        checkCudaErrors(cudaFree(d_ref));
-        return (float)(std::sqrt(sums[0] / sums[1]) * 100.0);
+        std::vector<double> sums(2 * slabs.size(), 0.0);
+        auto validation = Scenario::validation();
+        each_slab([&](Slab& s, int g) {
+            LBM_B200_CALL(lbm_recover_macroscopics(s.h));
+            const long long n = (long long)s.nyl * NX;
+            float2* d_ref = nullptr;
+            checkCudaErrors(cudaMalloc(&d_ref, (size_t)n * sizeof(float2)));
+            lbm_b200_shim::validation_functor_kernel<<<(unsigned)((n + 255) / 256), 256>>>(validation, d_ref, NX, s.y0, s.nyl);
+            checkCudaErrors(cudaGetLastError());
+            checkCudaErrors(cudaDeviceSynchronize());
+            LBM_B200_CALL(lbm_velocity_error_sums(s.h, reinterpret_cast<const float*>(d_ref), &sums[2 * (size_t)g]));
+            checkCudaErrors(cudaFree(d_ref));
+        });
+        double e = 0.0, r = 0.0;
+        for (size_t g = 0; g < slabs.size(); g++) { e += sums[2 * g]; r += sums[2 * g + 1]; }
+        return (float)(std::sqrt(e / r) * 100.0);
     }
 
     // extension: checkpoint / restart of the population state (lbm_checkpoint_write / lbm_checkpoint_read).  load_checkpoint
     // is called after allocate<S>() and init<S>() (which set flags, forces and bodies) and continues bit-identically.
+    // Several slabs: one file per slab, `path`.slab<g>.
     void save_checkpoint(const std::string& path) {
         flush(true);      // a pending step is closed WITH its rho / u: a following save_vtk() / update_macroscopics() finds them
-        LBM_B200_CALL(lbm_checkpoint_write(h, path.c_str()));
+        each_slab([&](Slab& s, int g) { LBM_B200_CALL(lbm_checkpoint_write(s.h, slab_path(path, g).c_str())); });
     }
     template <typename Scenario>
     void load_checkpoint(const std::string& path) {
         step_pending = false;
-        LBM_B200_CALL(lbm_checkpoint_read(h, path.c_str()));
+        each_slab([&](Slab& s, int g) { LBM_B200_CALL(lbm_checkpoint_read(s.h, slab_path(path, g).c_str())); });
         lbm_info_t inf;
         LBM_B200_CALL(lbm_info(h, &inf));
         timestep = inf.timestep;
@@ -407,23 +599,37 @@ public:
 
     // grid means of rho, rho|u|, |Pi| that the last CM<2,OptimalAdapter> step used (the reference's d_moment_avg)
     MomentInfo moment_avg() {
-        flush(true);      // a pending step is closed WITH its rho / u: a following save_vtk() / update_macroscopics() finds them
+        flush(true);
         float a[3];
         LBM_B200_CALL(lbm_moment_avg(h, a));
         return MomentInfo{a[0], a[1], a[2]};
     }
     double total_mass() {
-        flush(true);      // a pending step is closed WITH its rho / u: a following save_vtk() / update_macroscopics() finds them
-        double m = 0.0;
-        LBM_B200_CALL(lbm_total_mass(h, &m));
-        return m;
+        flush(true);
+        std::vector<double> m(slabs.size(), 0.0);
+        each_slab([&](Slab& s, int g) { LBM_B200_CALL(lbm_total_mass(s.h, &m[(size_t)g])); });
+        double t = 0.0;
+        for (double v : m) t += v;
+        return t;
     }
     void synchronize() {
-        flush(true);      // a pending step is closed WITH its rho / u: a following save_vtk() / update_macroscopics() finds them
-        LBM_B200_CALL(lbm_sync(h));
+        flush(true);
+        each_slab([&](Slab& s, int) { LBM_B200_CALL(lbm_sync(s.h)); });
     }
-    lbm_handle* handle() { return h; }
+    lbm_handle* handle(int slab = 0) { return slabs.at((size_t)slab).h; }
 
+private:
+    std::string slab_path(const std::string& path, int g) const { return slabs.size() == 1 ? path : path + ".slab" + std::to_string(g); }
+    const float* device_macroscopics(int which) {
+        if (slabs.size() != 1) { std::fprintf(stderr, "[LBM] get_rho() / get_u() are device views of ONE slab; with LBM_B200_GPUS > 1 use update_macroscopics() and h_rho / h_u\n"); std::exit(99); }
+        flush(true);
+        LBM_B200_CALL(lbm_recover_macroscopics(h));
+        const float *r = nullptr, *u = nullptr;
+        LBM_B200_CALL(lbm_get_macroscopics_device(h, &r, &u));
+        return which == 0 ? r : u;
+    }
+
+public:
     // raw dumps read by src/graphics/*.py: output/density/density_<t>.bin (NX*NY floats) and
     // output/velocity/velocity_<t>.bin (NX*NY*2 floats, AoS) — src/core/lbm.cuh:173-204
     void save_macroscopics(int ts) {
