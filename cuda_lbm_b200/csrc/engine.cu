@@ -91,6 +91,10 @@ struct lbm_handle {
     float* rho_out = nullptr; float2* u_out = nullptr; int macros_ts = -1;
     double* mass_acc = nullptr;
     double* val_stage = nullptr; long long val_stage_n = 0;      // validation reductions (lbm_*_error_sums, lbm_row_mean_velocity)
+    // odd phase through TMA (step_tma_kernel): a 3-D tensor map (x, row, plane) over the population allocation
+    alignas(64) CUtensorMap tmap{};
+    bool tma_ok = false;            // tensor map encoded, nx % 128 == 0, not disabled by LBM_B200_TMA=0
+    int tma_grid[4] = {0, 0, 0, 0}; // persistent grid per collision operator: SMs x resident blocks
     int timestep = 0;
     long long launches = 0;
     long long bytes = 0;
@@ -104,7 +108,7 @@ struct lbm_handle {
     // the device-side all-reduce of the adapter sums and the IBM node states of bodies across slab faces reach all of these
     struct Mapped { char* base = nullptr; void* ipc_base = nullptr; long long flags_off = 0, mail_off = -1; int y0 = 0, nyl = 0; } mapped[MAX_WORLD];
     SlabNet* d_net = nullptr;                      // device copy of the table the kernels use
-    bool all_mapped() const { for (int r = 0; r < cfg.world; r++) if (r != cfg.rank && !mapped[r].base) return false; return cfg.world > 1; }
+    bool attached_all = false;                     // lbm_peer_attach_all was called (by contract on EVERY slab): adapter sums are all-reduced on the device
     int adp_published_ts = -1;                     // lagged OptimalAdapter on several slabs: sums for this step are on their way to every slab's mailbox
     unsigned long long ibm_need_mask = 0;          // ranks that own stencil nodes of the bodies this slab works on
 };
@@ -161,7 +165,7 @@ static Params make_params(lbm_handle* h, int t) {
 // loaded up front instead, once per device, before any handle exists.
 template <typename K> static void preload(K kernel) { cudaFuncAttributes a; cudaFuncGetAttributes(&a, kernel); }
 template <int COLL> static void preload_coll() {
-    preload(step_vec_kernel<COLL, false>); preload(step_vec_kernel<COLL, true>);
+    preload(step_vec_kernel<COLL, false>); preload(step_vec_kernel<COLL, true>); preload(step_tma_kernel<COLL>);
     preload(step_kernel<COLL, false, false>); preload(step_kernel<COLL, false, true>);
     preload(step_kernel<COLL, true, false>); preload(step_kernel<COLL, true, true>);
 }
@@ -184,6 +188,35 @@ static void preload_kernels(int device) {
 }
 
 static dim3 grid_of(const lbm_handle* h) { return dim3((h->cfg.nx + BX - 1) / BX, h->nyl); }
+
+// Tensor map of the population planes for the TMA odd-phase kernel: dims (x = nx, row = nyl + 2, plane = nplanes), 128 x 1 x 1 boxes,
+// no swizzle, zero fill.  cuTensorMapEncodeTiled comes from the driver through the runtime's entry-point query, so the library keeps
+// linking against cudart only.  Any failure simply leaves the shuffle-based kernel in charge of the odd phase.
+template <int COLL> static int tma_resident_blocks() {
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, step_tma_kernel<COLL>, BX, TMA_SMEM_BYTES) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return nb;
+}
+static void setup_tma(lbm_handle* h) {
+    h->tma_ok = false;
+    if (const char* v = getenv("LBM_B200_TMA")) if (v[0] == '0') return;
+    if (h->cfg.nx % SEG != 0) return;
+    typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess || !fn) { cudaGetLastError(); return; }
+    const cuuint64_t dims[3] = {(cuuint64_t)h->cfg.nx, (cuuint64_t)(h->nyl + 2), (cuuint64_t)h->nplanes};
+    const cuuint64_t strides[2] = {(cuuint64_t)h->cfg.nx * 4, (cuuint64_t)h->plane * 4};
+    const cuuint32_t box[3] = {(cuuint32_t)SEG, 1, 1}, estr[3] = {1, 1, 1};
+    if (((encode_fn)fn)(&h->tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, h->pop, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, h->cfg.device) != cudaSuccess) { cudaGetLastError(); return; }
+    const int per_sm[4] = {tma_resident_blocks<C_BGK>(), tma_resident_blocks<C_MRT>(), tma_resident_blocks<C_CM>(), tma_resident_blocks<C_CMOPT>()};
+    for (int c = 0; c < 4; c++) { if (per_sm[c] < 1) return; h->tma_grid[c] = per_sm[c] * prop.multiProcessorCount; }
+    h->tma_ok = true;
+}
 
 extern "C" const char* lbm_last_error(void) { return g_err.c_str(); }
 
@@ -285,6 +318,7 @@ extern "C" int lbm_create(const lbm_config* cfg, lbm_handle** out) {
     h->ibm_mail = h->mail_nodes ? h->pop + pop_floats + TAIL_FIXED_BYTES / 4 : nullptr;
     cudaMemsetAsync(h->d_net, 0, sizeof(SlabNet), h->stream);
     cudaMemsetAsync(h->ring, 0, (size_t)2 * h->perim * Q * sizeof(float), h->stream);
+    setup_tma(h);
     float one[3] = {1.f, 1.f, 1.f};
     cudaMemcpyAsync(h->avg, one, sizeof(one), cudaMemcpyHostToDevice, h->stream);
     cudaStreamSynchronize(h->stream);

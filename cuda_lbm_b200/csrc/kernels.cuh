@@ -1,5 +1,6 @@
 // kernels.cuh — the __global__ kernels of the engine (see d2q9.cuh for the per-cell functions).
 #pragma once
+#include <cuda.h>           // CUtensorMap (the TMA odd-phase kernel)
 #include "d2q9.cuh"
 
 namespace lbm {
@@ -392,6 +393,194 @@ __global__ void __launch_bounds__(BX, vec_min_blocks(COLL, ODD)) step_vec_kernel
         }
     }
     if (COLL == C_CMOPT && p.partials) block_partials(s0, s1, s2, p.partials + 3 * ((long long)blockIdx.y * gridDim.x + blockIdx.x));
+}
+
+// ------------------------------------------------------------------ odd (neighbour) phase through the Tensor Memory Accelerator
+// The odd AA phase reads A[opp q][x - c_q] and writes A[q][x + c_q]: six of the nine slot planes are shifted by one cell in x, which
+// costs the kernel above ~280 of its ~1000 warp instructions per 128 cells (aligned float4 + lane shuffles + predicated scalar
+// accesses for the element that crosses a 16-byte boundary; ncu: profiles/r02_ncu_cmopt_before.md) and 36 staging registers.  TMA
+// tile copies take ELEMENT coordinates, so here the shift is part of the copy: per 128-cell segment one lane issues nine
+// cp.async.bulk.tensor loads of a 128 x 1 x 1 box at (x0 - c_x, y - c_y, opp q) into shared memory, every lane then reads its four
+// cells of each plane with one aligned LDS.128, collides, writes the results back in place, and nine tensor stores at
+// (x0 + c_x, y + c_y, q) put them where the next (even) step reads them.  Each WARP owns its segments, its shared-memory stages
+// and its mbarriers: no block-wide synchronisation.  Warps are persistent and prefetch the next segment's nine boxes while they
+// collide the current one, so the memory latency is covered by the copy engine instead of by occupancy.
+// Out-of-range box elements (x = -1 or nx on a row end) are zero-filled on load and clipped on store: the one element per row end
+// that wraps around periodically is loaded / stored by the lane that owns the cell, as a scalar access.
+#ifndef LBM_TMA_STAGES
+#define LBM_TMA_STAGES 2
+#endif
+#ifndef LBM_TMA_MIN_BLOCKS
+#define LBM_TMA_MIN_BLOCKS 4
+#endif
+constexpr int TMA_STAGES = LBM_TMA_STAGES;
+constexpr int TMA_WARPS = BX / 32;
+constexpr int TMA_STAGE_FLOATS = Q * SEG;                                 // nine 128-cell boxes = 4608 B
+constexpr int TMA_SMEM_BYTES = TMA_WARPS * TMA_STAGES * TMA_STAGE_FLOATS * 4 + TMA_WARPS * TMA_STAGES * 8;
+
+__device__ __forceinline__ unsigned smem_u32(const void* ptr) { return (unsigned)__cvta_generic_to_shared(ptr); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LBM_MBAR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra LBM_MBAR_DONE;\n"
+        "bra LBM_MBAR_WAIT;\n"
+        "LBM_MBAR_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_box(float* dst, const void* tmap, unsigned long long* bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"((unsigned long long)tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_store_box(const void* tmap, const float* src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"((unsigned long long)tmap), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// what the TMA kernel needs beyond Params: the rows it covers and where the two rest-population planes sit in the tensor
+struct TmaArgs {
+    int row_begin, row_end;     // local rows [row_begin, row_end): the slab without the edge rows that pull from a peer-mapped neighbour
+    int rest_plane[2];          // tensor plane index of A0[0] / A0[1]
+    float* partials;            // CM<2,OptimalAdapter>, lagged: one (rho, rho|u|, |Pi|) triple per block of THIS launch
+};
+
+template <int COLL>
+__global__ void __launch_bounds__(BX, LBM_TMA_MIN_BLOCKS) step_tma_kernel(const Params p, const __grid_constant__ CUtensorMap tmap, const TmaArgs a) {
+    extern __shared__ __align__(128) unsigned char tma_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* wbuf = reinterpret_cast<float*>(tma_smem) + warp * (TMA_STAGES * TMA_STAGE_FLOATS);
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(tma_smem + TMA_WARPS * TMA_STAGES * TMA_STAGE_FLOATS * 4) + warp * TMA_STAGES;
+    if (lane == 0) {
+#pragma unroll
+        for (int st = 0; st < TMA_STAGES; st++) mbar_init(&bars[st], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    float avg_raw[3] = {1.f, 1.f, 1.f};
+    if (COLL == C_CMOPT) { avg_raw[0] = __ldg(p.avg); avg_raw[1] = __ldg(p.avg + 1); avg_raw[2] = __ldg(p.avg + 2); }
+    const int gen = p.t & 1;
+    const int nsx = p.nsx;                                      // nx % 128 == 0 here: every segment is full
+    const int nseg = (a.row_end - a.row_begin) * nsx;
+    const int stride = gridDim.x * TMA_WARPS;
+    auto valid_from = [&](int sg) {                              // first segment >= sg (stepping by stride) the vectorised path owns
+        if (p.segmask)
+            while (sg < nseg && p.segmask[(long long)a.row_begin * nsx + sg] != 0) sg += stride;
+        return sg;
+    };
+    auto issue_loads = [&](int sg, int st) {                     // lane 0: nine boxes of segment sg into stage st
+        const int yl = a.row_begin + sg / nsx, x0 = (sg % nsx) * SEG;
+        float* dst = wbuf + st * TMA_STAGE_FLOATS;
+        mbar_expect_tx(&bars[st], TMA_STAGE_FLOATS * 4);
+        tma_load_box(dst, &tmap, &bars[st], x0, yl + 1, a.rest_plane[gen]);
+#pragma unroll
+        for (int q = 1; q < Q; q++) {
+            int ys = yl - cy(q);                                 // g_q(x) = A[opp q][x - c_q]
+            if (p.wrap_y) { if (ys < 0) ys += p.nyl; else if (ys >= p.nyl) ys -= p.nyl; }
+            tma_load_box(dst + q * SEG, &tmap, &bars[st], x0 - cx(q), ys + 1, opp(q));
+        }
+    };
+    const Relax rx = relax_of(p);
+    const bool forced = p.fx != 0.0f || p.fy != 0.0f;
+    const V2 Fx = splat<V2>(p.fx), Fy = splat<V2>(p.fy);
+    AdapterAvg av{};
+    if (COLL == C_CMOPT) { av.inv_rho = 1.0f / avg_raw[0]; av.inv_j = 1.0f / avg_raw[1]; av.inv_pi = 1.0f / avg_raw[2]; }
+    V2 acc0 = splat<V2>(0.f), acc1 = acc0, acc2 = acc0;
+
+    int sg = valid_from(blockIdx.x * TMA_WARPS + warp);
+    int st = 0;
+    unsigned phase = 0;                                         // bit st = parity the next wait on stage st expects
+    if (sg < nseg && lane == 0) issue_loads(sg, 0);
+    while (sg < nseg) {
+        const int nxt = valid_from(sg + stride);
+        if (nxt < nseg && lane == 0) {
+            tma_wait_read_all();                                // the stores that read the other stage (previous segment) are through with it
+            issue_loads(nxt, (st + 1) % TMA_STAGES);
+        }
+        const int yl = a.row_begin + sg / nsx, x0 = (sg % nsx) * SEG + 4 * lane;
+        float* buf = wbuf + st * TMA_STAGE_FLOATS + 4 * lane;
+        int ym = yl - 1, yp = yl + 1;
+        if (p.wrap_y) { if (ym < 0) ym += p.nyl; if (yp >= p.nyl) yp -= p.nyl; }
+        // the two elements per row that wrap around periodically in x: scalar loads, issued before the wait
+        const bool first = x0 == 0, last = x0 + 4 == p.nx;
+        float wl[3] = {0.f, 0.f, 0.f}, wr[3] = {0.f, 0.f, 0.f};
+        if (first) {        // q with c_x = +1 (1, 5, 8) pull from x = -1 -> nx - 1 of plane opp q, row y - c_y
+            wl[0] = p.A[3][rowoff(p, yl) + p.nx - 1]; wl[1] = p.A[7][rowoff(p, ym) + p.nx - 1]; wl[2] = p.A[6][rowoff(p, yp) + p.nx - 1];
+        }
+        if (last) {         // q with c_x = -1 (3, 6, 7) pull from x = nx -> 0
+            wr[0] = p.A[1][rowoff(p, yl)]; wr[1] = p.A[8][rowoff(p, ym)]; wr[2] = p.A[5][rowoff(p, yp)];
+        }
+        mbar_wait(&bars[st], (phase >> st) & 1u);
+        phase ^= 1u << st;
+        V2 g[2][Q];
+#pragma unroll
+        for (int q = 0; q < Q; q++) {
+            const float4 v = *reinterpret_cast<const float4*>(buf + q * SEG);
+            g[0][q].a = make_float2(v.x, v.y); g[1][q].a = make_float2(v.z, v.w);
+        }
+        if (first) { g[0][1].a.x = wl[0]; g[0][5].a.x = wl[1]; g[0][8].a.x = wl[2]; }
+        if (last) { g[1][3].a.y = wr[0]; g[1][6].a.y = wr[1]; g[1][7].a.y = wr[2]; }
+        float2 rho4[2], ux4[2], uy4[2];
+#pragma unroll
+        for (int hf = 0; hf < 2; hf++) {
+            const Mom<V2> m = moments_v(g[hf]);
+            V2 ux = m.ux, uy = m.uy;
+            if (forced) { const V2 hr = m.inv_rho * 0.5f; ux = fma(Fx, hr, ux); uy = fma(Fy, hr, uy); }
+            rho4[hf] = m.rho.a; ux4[hf] = ux.a; uy4[hf] = uy.a;
+            if (COLL == C_BGK) collide_bgk_v(rx, g[hf], m.rho, ux, uy, forced, Fx, Fy);
+            else if (COLL == C_MRT) collide_mrt_v(rx, g[hf], m.rho, ux, uy, forced, Fx, Fy);
+            else if (COLL == C_CM) collide_cm_v<false>(rx, g[hf], ux, uy, forced, Fx, Fy, splat<V2>(1.0f));
+            else {
+                const V2 jm = jmag_v(ux, uy, m.rho), pm = pi_norm_v(m);
+                acc0 = acc0 + m.rho; acc1 = acc1 + jm; acc2 = acc2 + pm;
+                collide_cm_v<true>(rx, g[hf], ux, uy, forced, Fx, Fy, optimal_rate_v(m.rho, jm, pm, av));
+            }
+        }
+        if (p.rho_out) {
+            const long long ln = (long long)yl * p.nx + x0;
+            st4(p.rho_out + ln, rho4[0].x, rho4[0].y, rho4[1].x, rho4[1].y);
+            float* uo = reinterpret_cast<float*>(p.u_out + ln);
+            st4(uo, ux4[0].x, uy4[0].x, ux4[0].y, uy4[0].y);
+            st4(uo + 4, ux4[1].x, uy4[1].x, ux4[1].y, uy4[1].y);
+        }
+        // results back into the stage, in place (a lane reads and writes only its own 16 bytes of every box)
+#pragma unroll
+        for (int q = 0; q < Q; q++)
+            *reinterpret_cast<float4*>(buf + q * SEG) = make_float4(g[0][q].a.x, g[0][q].a.y, g[1][q].a.x, g[1][q].a.y);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+            const int xs = (sg % nsx) * SEG;
+            const float* src = wbuf + st * TMA_STAGE_FLOATS;
+            tma_store_box(&tmap, src, xs, yl + 1, a.rest_plane[gen]);
+#pragma unroll
+            for (int q = 1; q < Q; q++)                         // f*_q(x) -> A[q][x + c_q]
+                tma_store_box(&tmap, src + q * SEG, xs + cx(q), (cy(q) > 0 ? yp : (cy(q) < 0 ? ym : yl)) + 1, q);
+            tma_commit();
+        }
+        // the clipped ends: f*_q of cell nx-1 with c_x = +1 goes to x = 0, of cell 0 with c_x = -1 to x = nx-1
+        if (last) {
+            p.A[1][rowoff(p, yl)] = g[1][1].a.y; p.A[5][rowoff(p, yp)] = g[1][5].a.y; p.A[8][rowoff(p, ym)] = g[1][8].a.y;
+        }
+        if (first) {
+            p.A[3][rowoff(p, yl) + p.nx - 1] = g[0][3].a.x; p.A[6][rowoff(p, yp) + p.nx - 1] = g[0][6].a.x; p.A[7][rowoff(p, ym) + p.nx - 1] = g[0][7].a.x;
+        }
+        sg = nxt;
+        st = (st + 1) % TMA_STAGES;
+    }
+    if (lane == 0) tma_wait_all();                              // the bulk stores must have landed before the block gives up its shared memory
+    if (COLL == C_CMOPT && a.partials) block_partials(hsum(acc0), hsum(acc1), hsum(acc2), a.partials + 3 * (long long)blockIdx.x);
 }
 
 // moments pre-pass for LBM_ADAPTER_EXACT: the grid sums of the CURRENT post-stream state, before any cell collides.

@@ -425,3 +425,68 @@ def test_run_from_host_on_peer_mapped_slabs(nx, ny, world, coll, nsteps):
     for e in engs:
         e.close()
     assert np.array_equal(fs, f1)
+
+
+# ---------------------------------------------------------------- odd phase through TMA (nx a multiple of 128)
+def _steps_fields(case, nsteps, quirks=63, adapter_mode=0, tma=True):
+    import os
+    old = os.environ.get("LBM_B200_TMA")
+    os.environ["LBM_B200_TMA"] = "1" if tma else "0"       # read by lbm_create
+    try:
+        e = make_engine(case, quirks, adapter_mode)
+    finally:
+        if old is None:
+            del os.environ["LBM_B200_TMA"]
+        else:
+            os.environ["LBM_B200_TMA"] = old
+    e.init_fields(*case.init_fields())
+    e.step(nsteps, macroscopics=True)
+    out = e.macroscopics(), e.populations()
+    e.close()
+    return out
+
+
+TMA_CASES = [("tg", 256, 48, (True, True), cases.BGK), ("tg", 384, 40, (True, True), cases.MRT), ("tg", 128, 36, (True, True), cases.CM),
+             ("tg", 512, 24, (True, True), cases.CM_OPT), ("pois", 256, 24, (True, False), cases.MRT), ("lid", 384, 40, (False, False), cases.CM_OPT),
+             ("cyl_ibm", 384, 64, (False, False), cases.MRT), ("cyl_flag", 256, 64, (False, False), cases.BGK)]
+
+
+@pytest.mark.parametrize("kind,nx,ny,periodic,coll", TMA_CASES)
+def test_tma_odd_phase_equals_the_shuffle_kernel_and_the_oracle(kind, nx, ny, periodic, coll):
+    """Grids whose rows are whole 128-cell segments take the odd AA phase through step_tma_kernel (tensor-map tile copies with the
+    one-cell x shift in the box coordinates).  Same per-cell arithmetic as the shuffle-based kernel: bit-identical fields; and the
+    usual fp32 bounds against the CPU oracle."""
+    nu = 1.0 / 6.0 if kind in ("tg", "pois") else (0.03 if kind == "lid" else float(cases._cyl_nu(ny)))
+    um = {"tg": 0.04, "pois": 0.05, "lid": 0.1}.get(kind, 0.05)
+    force = cases._pois_force(ny) if kind == "pois" else (0.0, 0.0)
+    case = cases.Case(f"tma_{kind}_{nx}x{ny}", nx, ny, coll, nu, periodic, um, kind, force=force, np_markers=24, scale=nx // 128)
+    n = 9
+    (rho_t, u_t), f_t = _steps_fields(case, n, tma=True)
+    (rho_s, u_s), f_s = _steps_fields(case, n, tma=False)
+    assert np.isfinite(f_t).all()
+    assert np.array_equal(f_t, f_s) and np.array_equal(rho_t, rho_s) and np.array_equal(u_t, u_s), float(np.abs(f_t - f_s).max())
+    o = make_oracle(case)
+    o.init(*case.init_fields())
+    o.step(n)
+    assert np.abs(f_t - o.populations()).max() <= TOL_F * n ** 0.5
+    assert np.abs(rho_t - o.macroscopics()[0]).max() <= TOL_RHO * n ** 0.5
+
+
+@pytest.mark.parametrize("coll,world,chunk,direct", [(cases.BGK, 2, 7, True), (cases.MRT, 3, 4, True), (cases.CM_OPT, 3, 7, "all"), (cases.CM, 2, 1, False)])
+def test_tma_odd_phase_on_slabs(coll, world, chunk, direct):
+    """Slabs: interior rows take the TMA kernel, the two rows that pull from a peer-mapped neighbour the shuffle kernel (one-row bands)."""
+    case = cases.Case("tma_slabs", 256, 36, coll, 1.0 / 6.0, (True, True), 0.04, "tg", scale=2)
+    nsteps = 7
+    rho_s, u_s, f_s = _run_slabs(case, world, nsteps, direct=direct, chunk=chunk)
+    (rho_1, u_1), f_1 = _steps_fields(case, nsteps)
+    tol = 0.0 if coll != cases.CM_OPT else 2e-7
+    assert np.abs(f_s - f_1).max() <= tol and np.abs(rho_s - rho_1).max() <= tol and np.abs(u_s - u_1).max() <= tol
+
+
+def test_tma_lagged_adapter_partials():
+    """LBM_ADAPTER_LAGGED: the TMA kernel forms one partial triple per persistent block, the shuffle kernel one per 512 cells — the
+    grid means agree to fp32 summation order."""
+    case = cases.Case("tma_lag", 512, 64, cases.CM_OPT, 0.03, (False, False), 0.1, "lid")
+    (rho_t, u_t), f_t = _steps_fields(case, 12, adapter_mode=1, tma=True)
+    (rho_s, u_s), f_s = _steps_fields(case, 12, adapter_mode=1, tma=False)
+    assert np.isfinite(f_t).all() and np.abs(f_t - f_s).max() <= 1e-6, float(np.abs(f_t - f_s).max())

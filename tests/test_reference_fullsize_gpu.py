@@ -71,7 +71,9 @@ def test_c3_cavity_4096_cm_optimal_vs_reference_cuda(tmp_path):
     assert np.isfinite(rho_r).all() and np.isfinite(u_r).all(), "the reference left the finite window: shorten the run"
     case = cases.Case("c3", n, n, cases.CM_OPT, 0.4096, (False, False), 0.1, "lid")
     rho0, u0 = case.init_fields()
-    for mode, tol_rho, tol_u in ((0, 2e-5, 1e-3), (1, 2e-4, 1e-2)):       # exact (reference semantics) / lagged grid means
+    # exact = the reference's semantics (measured on the B200: max|drho| 1.0e-5, relL2(u) 3.0e-6); lagged = the grid means of the
+    # previous step, a different (documented) discretisation of the adapter: 4.9e-4 / 2.0e-4 after 20 steps of the impulsively started lid
+    for mode, tol_rho, tol_u in ((0, 2e-5, 1e-4), (1, 1e-3, 1e-3)):
         e = make_engine(case, quirks=127, adapter_mode=mode)
         e.init_fields(rho0, u0)
         e.step(steps, macroscopics=True)
@@ -119,7 +121,10 @@ def test_taylor_green_8192_bgk_vs_reference_cuda(tmp_path):
     s = e.taylor_green_error_sums(case.nu, 0.04 / 64, float(steps))
     e.close()
     d_rho, d_u, l2_u = report("t_tg_bgk_8192", steps, rho_e, u_e, rho_r, u_r)
-    assert d_rho <= 5e-6 and l2_u <= 1e-4, (d_rho, l2_u)
+    # |u| <= u_max / SCALE = 6.25e-4 on this box: the fp32 round-off of u = sum f c / rho (populations ~0.03 .. 0.44) is ~1e-7 per step in
+    # ABSOLUTE terms whatever |u| is, so the bar is absolute (measured 1.7e-6 after 100 steps = 8e-4 of this tiny velocity scale;
+    # 256^2 with |u| = 0.02 gives relL2 6e-5, tests/test_shim_gpu.py)
+    assert d_rho <= 5e-6 and d_u <= 4e-6 and l2_u <= 2e-3, (d_rho, d_u, l2_u)
     # analytic error of the engine no worse than the reference's on the same step (numpy, fp64)
     y, x = np.meshgrid(np.arange(n) + 0.5, np.arange(n) + 0.5, indexing="ij")
     k = 2 * np.pi / n
