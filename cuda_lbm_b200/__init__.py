@@ -2,11 +2,9 @@
 
 csrc/        CUDA kernels (sm_100a) + the C ABI declared in include/lbm_b200.h -> liblbm_b200.so
 _capi.py     ctypes declarations of that ABI (no CPU fallback: import fails if the library is missing)
-solver.py    Engine (one handle) and LBM, the mirror of the reference's LBM<2> driver protocol
-scenarios.py ScenarioTrait and the four 2-D scenarios of src/scenarios/
+solver.py    Engine: one handle of the C ABI with numpy in / out (tests, bench.py, the multi-process launcher)
 slab.py      y-slab decomposition over the GPUs of one box (torch.distributed / NCCL halo exchange)
 """
 from ._capi import (ADAPTER_EXACT, ADAPTER_LAGGED, BGK, CM, CM_OPTIMAL, MRT, QK_FIXED, QK_REFERENCE, LbmError,  # noqa: F401
                     lib)
-from .solver import LBM, Engine, default_S  # noqa: F401
-from . import scenarios  # noqa: F401
+from .solver import Engine, default_S  # noqa: F401

@@ -29,7 +29,7 @@ SYMBOLS = [
     "lbm_set_moment_sums", "lbm_get_moment_sums", "lbm_info", "lbm_next_step_needs_halo", "lbm_halo_pack_pre",
     "lbm_halo_unpack_pre", "lbm_halo_pack_post", "lbm_halo_unpack_post", "lbm_peer_export", "lbm_peer_attach", "lbm_peer_attach_all", "lbm_peer_detach",
     "lbm_host_alloc", "lbm_host_free",
-    "lbm_velocity_error_sums", "lbm_taylor_green_error_sums", "lbm_row_mean_velocity",
+    "lbm_velocity_error_sums", "lbm_taylor_green_error_sums", "lbm_row_mean_velocity", "lbm_sample_velocity",
     "lbm_checkpoint_bytes", "lbm_checkpoint_write", "lbm_checkpoint_read",
     "lbm_ibm_exchange_floats", "lbm_ibm_pack", "lbm_ibm_unpack", "lbm_set_body_velocities", "lbm_move_body",
     "lbm_run_from_host", "lbm_recover_macroscopics", "lbm_adapter_sums_pending",
@@ -113,6 +113,7 @@ def lib():
         "lbm_velocity_error_sums": [vp, vp, dp],
         "lbm_taylor_green_error_sums": [vp, C.c_float, C.c_float, C.c_float, dp],
         "lbm_row_mean_velocity": [vp, dp, dp],
+        "lbm_sample_velocity": [vp, C.POINTER(C.c_int64), C.c_int32, fp],
         "lbm_checkpoint_bytes": [vp, C.POINTER(C.c_int64)],
         "lbm_checkpoint_write": [vp, C.c_char_p],
         "lbm_checkpoint_read": [vp, C.c_char_p],

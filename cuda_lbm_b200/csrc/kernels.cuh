@@ -1137,6 +1137,14 @@ __global__ void __launch_bounds__(256) error_sums_final_kernel(const double* sta
     for (int i = threadIdx.x; i < n; i += 256) { e += stage[2 * i]; r += stage[2 * i + 1]; }
     block_sum2(e, r, out);
 }
+// u at a list of global nodes (the samples of a centre-line validation: LidDrivenScenario::compute_error reads 2 x 17 of them from
+// h_u, lidDrivenCavityScenario.cuh:103-135); nodes other slabs own are left untouched
+__global__ void sample_velocity_kernel(const float2* u, const long long* nodes, int n, long long first, long long nloc, float2* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const long long ln = nodes[i] - first;
+    if (ln >= 0 && ln < nloc) out[i] = u[ln];
+}
 // mean of u over x for every row of the slab (the inner loop of PoiseuilleScenario::compute_error, poiseuilleScenario.cuh:63-70)
 __global__ void __launch_bounds__(256) row_mean_kernel(const float2* u, int nx, double* mean_ux, double* mean_uy) {
     const float2* row = u + (long long)blockIdx.x * nx;

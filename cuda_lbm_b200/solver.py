@@ -1,12 +1,6 @@
-"""Host-side mirror of the reference's solver interface over the C ABI.
-
-`Engine`  — one handle of include/lbm_b200.h with numpy in/out.
-`LBM`     — the reference's `LBM<2>` (src/core/lbm.cuh:33-382) with the same method names and the
-            same driver protocol as src/main.cu:72-153: allocate(S), init(S), then per step
-            increase_ts / stream / swap_buffers / apply_boundaries / uncorrected_macroscopics /
-            reset_forces / ibm_step / correct_macroscopics / compute_equilibrium / collide, and
-            occasionally update_macroscopics / compute_error.  The nine per-kernel methods only
-            record the step; the fused kernel runs once per step when the step is closed.
+"""`Engine` — one handle of the C ABI (include/lbm_b200.h) with numpy in / out: what the parity tests, bench.py and the
+multi-process launcher (slab.py) drive.  The reference-facing host interface is C++ (include/cuda-lbm/: LBM<2>, ScenarioTrait);
+a Python mirror of that driver protocol, used by a development tool only, lives in tools/pyscenarios.py.
 """
 import ctypes as C
 
@@ -202,6 +196,13 @@ class Engine:
         check(lib().lbm_row_mean_velocity(self._h, mx.ctypes.data_as(dp), my.ctypes.data_as(dp)))
         return mx, my
 
+    def sample_velocity(self, nodes, out=None):
+        """u at the listed global nodes, [n, 2]; entries of nodes another slab owns keep the values of `out` (zeros by default)."""
+        nodes = np.ascontiguousarray(nodes, np.int64).reshape(-1)
+        out = np.zeros((nodes.size, 2), np.float32) if out is None else np.ascontiguousarray(out, np.float32)
+        check(lib().lbm_sample_velocity(self._h, nodes.ctypes.data_as(C.POINTER(C.c_int64)), nodes.size, _fp(out)))
+        return out
+
     # --- checkpoint / restart ---
     def checkpoint_bytes(self):
         n = C.c_int64()
@@ -251,100 +252,3 @@ class Engine:
     def halo(self, what, side, ptr):
         fn = getattr(lib(), "lbm_halo_" + what)
         check(fn(self._h, side, C.c_void_p(ptr)))
-
-
-class LBM:
-    """Drop-in for the reference's `LBM<2>` object (see module docstring).  `Scenario` objects follow
-    cuda_lbm_b200.scenarios.ScenarioTrait, the mirror of src/scenarios/scenario.cuh:22-78."""
-
-    def __init__(self, nx, ny, device=0, quirks=capi.QK_REFERENCE, adapter_mode=capi.ADAPTER_EXACT):
-        self.NX, self.NY = nx, ny
-        self.device, self.quirks, self.adapter_mode = device, quirks, adapter_mode
-        self.timestep = 0
-        self.update_ts = 0
-        self.h_rho = np.zeros(nx * ny, np.float32)
-        self.h_u = np.zeros(2 * nx * ny, np.float32)
-        self.engine = None
-        self._pending = False
-
-    # LBM::allocate<Scenario>()  lbm.cuh:92-125
-    def allocate(self, S):
-        self.engine = Engine(self.NX, self.NY, collision=S.collision, viscosity=S.viscosity, S=S.S, periodic=S.periodic,
-                             u_max=S.u_max, force=S.body_force(self.NX, self.NY), quirks=self.quirks,
-                             adapter_mode=self.adapter_mode, device=self.device)
-        S.IBM_bodies.clear()
-        S.add_bodies(self.NX, self.NY)
-        for body in S.IBM_bodies:
-            self.engine.add_body(body)
-
-    # LBM::init<Scenario>()  init.cuh:45-86
-    def init(self, S):
-        init = S.init(self.NX, self.NY)
-        rho, u = init()
-        boundary = S.boundary(self.NX, self.NY)
-        yy, xx = np.meshgrid(np.arange(self.NY), np.arange(self.NX), indexing="ij")
-        self.engine.set_flags(boundary(xx, yy))
-        self.engine.init_fields(rho, u)
-        self.timestep = 0
-        self._pending = False
-
-    def _close_step(self, macroscopics=False):
-        if self._pending:
-            self.engine.step(1, macroscopics=macroscopics)
-            self._pending = False
-
-    def increase_ts(self, S=None):
-        self._close_step()
-        self.timestep += 1
-        if S is not None:
-            S.update_ts(self.timestep)
-
-    # the reference's per-kernel host methods (lbm.cuh:345-377): recorded, executed fused
-    def stream(self): pass
-    def swap_buffers(self): pass
-    def apply_boundaries(self, S=None): pass
-    def uncorrected_macroscopics(self): pass
-    def reset_forces(self, S=None): pass
-    def ibm_step(self): pass
-    def correct_macroscopics(self): pass
-    def compute_equilibrium(self): pass
-
-    def collide(self, op=None):
-        self._pending = True
-
-    def run(self, nsteps, S=None):
-        """nsteps iterations of the main.cu loop body without the per-call overhead."""
-        self._close_step()
-        if nsteps > 0:
-            self.engine.step(nsteps - 1)
-            self.timestep += nsteps
-            self._pending = True
-            if S is not None:
-                S.update_ts(self.timestep)
-
-    # LBM::update_macroscopics()  lbm.cuh:148-154
-    def update_macroscopics(self):
-        if self._pending:
-            self._close_step(macroscopics=True)
-        rho, u = self.engine.macroscopics()
-        self.h_rho[:] = rho.reshape(-1)
-        self.h_u[:] = u.reshape(-1)
-        self.update_ts = self.timestep
-
-    def get_rho(self):
-        return self.h_rho
-
-    def get_u(self):
-        return self.h_u
-
-    # LBM::compute_error<Scenario>()  lbm.cuh:163-171
-    def compute_error(self, S):
-        if S.has_analytical_solution:
-            return S.compute_error(self)
-        print("Scenario does not provide verification/validation.")
-        return 0.0
-
-    def free(self):
-        if self.engine is not None:
-            self.engine.close()
-            self.engine = None

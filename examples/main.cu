@@ -119,6 +119,9 @@ int main(int argc, char** argv) {
         if constexpr (Scenario::has_analytical_solution) {
             last_error = lbm.compute_error<Scenario>();
             printf("%s[%d]: error, %.4f%%\n", Scenario::name(), first_step + t, last_error);
+            if constexpr (lbm_b200_shim::is_centerline_validation<typename Scenario::ValidationType>::value)
+                printf("%s[%d]: centre-line NRMSE against Ghia et al. with the samples gathered on the device, %.4f%%\n", Scenario::name(), first_step + t,
+                       lbm.centerline_error_device<Scenario>());
 #ifndef LBM_B200_NO_DEVICE_ERROR      // needs a __host__ __device__ Validation::operator()(x, y, ux&, uy&), as the reference's are
             if constexpr (lbm_b200_shim::is_field_validation<typename Scenario::ValidationType>::value)
                 printf("%s[%d]: L2 error taken on the device, %.4f%%\n", Scenario::name(), first_step + t, lbm.l2_error_device<Scenario>());

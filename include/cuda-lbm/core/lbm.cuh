@@ -116,6 +116,11 @@ template <typename V, typename = void> struct is_field_validation : std::false_t
 template <typename V>
 struct is_field_validation<V, std::void_t<decltype(std::declval<const V&>()(0, 0, std::declval<float&>(), std::declval<float&>()))>> : std::true_type {};
 
+// does it carry the centre-line tables of the reference's LidDrivenValidation (lidDrivenCavityFunctors.cuh:58-221)?
+template <typename V, typename = void> struct is_centerline_validation : std::false_type {};
+template <typename V>
+struct is_centerline_validation<V, std::void_t<decltype(V::ghia_u_count), decltype(std::declval<const V&>().get_closest_ref_data(0, true))>> : std::true_type {};
+
 inline int env_int(const char* name, int fallback) {
     const char* v = std::getenv(name);
     return v ? std::atoi(v) : fallback;
@@ -577,6 +582,49 @@ public:
         double e = 0.0, r = 0.0;
         for (size_t g = 0; g < slabs.size(); g++) { e += sums[2 * g]; r += sums[2 * g + 1]; }
         return (float)(std::sqrt(e / r) * 100.0);
+    }
+
+    // extension: u[2*i + c] at the listed global nodes, gathered on the device (2 floats per node cross PCIe instead of the field)
+    std::vector<float> sample_velocity(const std::vector<long long>& nodes) {
+        flush(true);
+        std::vector<float> out(2 * nodes.size(), 0.0f);
+        static_assert(sizeof(long long) == sizeof(int64_t), "node ids are 64-bit");
+        for (Slab& s : slabs) {
+            if (slabs.size() > 1) checkCudaErrors(cudaSetDevice(s.device));
+            LBM_B200_CALL(lbm_recover_macroscopics(s.h));
+            LBM_B200_CALL(lbm_sample_velocity(s.h, reinterpret_cast<const int64_t*>(nodes.data()), (int32_t)nodes.size(), out.data()));
+        }
+        if (slabs.size() > 1) checkCudaErrors(cudaSetDevice(home_device));
+        return out;
+    }
+
+    // extension: the centre-line metric of LidDrivenScenario::compute_error (src/scenarios/lidDrivenCavity/lidDrivenCavityScenario.cuh:88-157:
+    // NRMSE of u_x on the vertical and u_y on the horizontal centre line against the tables of Ghia, Ghia & Shin 1982, mean of the two,
+    // in percent) with the 2 x 17 samples gathered on the device.  Works with any Validation functor that has the reference's table
+    // interface (ghia_u_count, ghia_x, ghia_y, get_closest_ref_data).
+    template <typename Scenario>
+    float centerline_error_device() {
+        const auto validator = Scenario::validation();
+        const int re = (int)compute_reynolds(Scenario::u_max, NY, Scenario::viscosity);
+        const float* ux_ref = validator.get_closest_ref_data(re, true);
+        const float* uy_ref = validator.get_closest_ref_data(re, false);
+        const int n = validator.ghia_u_count;
+        std::vector<long long> nodes((size_t)2 * n);
+        for (int i = 0; i < n; i++) {
+            int y = (int)std::round(validator.ghia_y[i] * (NY - 1)), x = (int)std::round(validator.ghia_x[i] * (NX - 1));
+            y = std::max(0, std::min(y, NY - 1)); x = std::max(0, std::min(x, NX - 1));
+            nodes[(size_t)i] = (long long)y * NX + NX / 2;
+            nodes[(size_t)n + i] = (long long)(NY / 2) * NX + x;
+        }
+        const std::vector<float> u = sample_velocity(nodes);
+        float ex = 0.0f, rx = 0.0f, ey = 0.0f, ry = 0.0f;
+        for (int i = 0; i < n; i++) {
+            const float dx = u[2 * (size_t)i] * (1.0f / Scenario::u_max) - ux_ref[i], dy = u[2 * ((size_t)n + i) + 1] * (1.0f / Scenario::u_max) - uy_ref[i];
+            ex += dx * dx; rx += ux_ref[i] * ux_ref[i];
+            ey += dy * dy; ry += uy_ref[i] * uy_ref[i];
+        }
+        const float rmse_x = rx > 0.0f ? std::sqrt(ex / rx) : 0.0f, rmse_y = ry > 0.0f ? std::sqrt(ey / ry) : 0.0f;
+        return 100.0f * (rmse_x + rmse_y) / 2.0f;
     }
 
     // extension: checkpoint / restart of the population state (lbm_checkpoint_write / lbm_checkpoint_read).  load_checkpoint

@@ -226,6 +226,11 @@ int lbm_taylor_green_error_sums(lbm_handle* h, float nu, float u0, float t, doub
  * PoiseuilleScenario::compute_error (src/scenarios/poiseuille/poiseuilleScenario.cuh:63-70). */
 int lbm_row_mean_velocity(lbm_handle* h, double* mean_ux_rows, double* mean_uy_rows);
 
+/* u[node*2+c] at n listed GLOBAL nodes (host arrays): what a centre-line validation reads from h_u — LidDrivenScenario::compute_error
+ * compares 2 x 17 samples with the tables of Ghia et al. (src/scenarios/lidDrivenCavity/lidDrivenCavityScenario.cuh:88-157) — without
+ * moving the whole field to the host.  Entries whose node belongs to another slab keep the caller's values: call it on every slab. */
+int lbm_sample_velocity(lbm_handle* h, const int64_t* nodes, int32_t n, float* u_out_aos);
+
 /* ---- checkpoint / restart (no reference counterpart) ------------------------------
  * lbm_checkpoint_write stores the populations of this slab as they sit in HBM, the edge ring, the time step and the
  * adapter means in one file (lbm_checkpoint_bytes long), streamed through pinned staging buffers; lbm_checkpoint_read

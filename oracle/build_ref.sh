@@ -17,6 +17,7 @@
 #   P5  lbm_constants.cuh:298  drop the unconditional `#define SOA`  (2-D code is AoS-only)
 #   P6  streaming.cuh:9-10 PERIODIC_X/Y selectable with -DREF_PERIODIC_X/-DREF_PERIODIC_Y
 #   P8  adapters.cuh:101-107  remove the per-node printf of OptimalAdapter
+#   P10 flowPastCylinderScenario.cuh:12  `BGK` -> `BGK<2>`            (build fix; only the s_cyl_* binary includes that file)
 # None of them changes the arithmetic of the path.
 set -euo pipefail
 REF=${REF:-/root/reference}
@@ -60,6 +61,9 @@ sed -i '298s|^#define SOA|// #define SOA (P5)|' "$S/core/lbm_constants.cuh"
 # P6
 sed -i '9s|^// #define PERIODIC_X|#ifdef REF_PERIODIC_X\n#define PERIODIC_X\n#endif|; 10s|^// #define PERIODIC_Y|#ifdef REF_PERIODIC_Y\n#define PERIODIC_Y\n#endif|' "$S/core/streaming/streaming.cuh"
 grep -q 'REF_PERIODIC_Y' "$S/core/streaming/streaming.cuh"
+# P10 (build fix only): flowPastCylinderScenario.cuh:12 names the collision template without its argument
+sed -i '12s/BGK/BGK<2>/' "$S/scenarios/flowPastCylinder/flowPastCylinderScenario.cuh"
+grep -q 'BGK<2>' "$S/scenarios/flowPastCylinder/flowPastCylinderScenario.cuh"
 # P8
 sed -i '101,107d' "$S/core/collision/adapters.cuh"
 ! grep -q 'new_tau_star' "$S/core/collision/adapters.cuh"

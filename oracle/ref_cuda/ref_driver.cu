@@ -19,6 +19,8 @@
 //                3 cavity with ZOU_HE_TOP lid + BOUNCE_BACK walls (older variant, lidDrivenCavityFunctors.cuh:41-53 comments)
 //                4 flow past cylinder, IBM markers        flowPastCylinderScenario.cuh (P10)
 //                5 flow past cylinder, CYLINDER flag nodes + PRESSURE_OUTLET
+//                6 the reference's OWN flowPastCylinderScenario.cuh as it is (two 16-marker cylinders, BGK<2> after the one-token build
+//                  fix of SURVEY.md A-D5), for tests/test_shim_gpu.py::test_reference_cylinder_scenario_...
 //   -DREF_COLL=  0 BGK<2>  1 MRT<2>  2 CM<2,NoAdapter>  3 CM<2,OptimalAdapter>
 //   -DREF_UMAX= -DREF_VISC=        scenario constants (optional)
 //   -DREF_NP=                      markers per cylinder (case 4)
@@ -76,7 +78,10 @@ using Coll = CM<2, OptimalAdapter>;
 #define REF_S(om) {0.0f, om, om, 0.0f, om, 0.0f, om, om, om}
 #endif
 
-#if REF_CASE == 0
+#if REF_CASE == 6
+#include "scenarios/flowPastCylinder/flowPastCylinderScenario.cuh"
+using Scenario = FlowPastCylinderScenario;
+#elif REF_CASE == 0
 #ifndef REF_UMAX
 #define REF_UMAX 0.04f
 #endif

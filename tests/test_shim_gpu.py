@@ -63,7 +63,10 @@ def rel_l2(a, b):
 # measured on the B200 (profiles/r01_shim_parity.txt): TG 6.0e-5, the others below 1e-5
 PAIRS = [("ref_tg_256", "c1_tg_bgk_256", 256, 256, 1000, 5e-6, 1e-4),
          ("ref_lid_129", "s_lid_bgk_129", 129, 129, 1000, 2e-5, 1e-4),
-         ("ref_pois_150x100", "s_pois_bgk_150x100", 150, 100, 500, 2e-5, 2e-4)]
+         ("ref_pois_150x100", "s_pois_bgk_150x100", 150, 100, 500, 2e-5, 2e-4),
+         # the reference's flowPastCylinderScenario.cuh (two 16-marker IBM cylinders, Zou-He inlet, zero-gradient outflow) after the
+         # one-token build fix it needs in the reference too (`BGK` -> `BGK<2>`)
+         ("ref_cyl_256x128", "s_cyl_bgk_256x128", 256, 128, 500, 2e-5, 2e-4)]
 
 
 @pytest.mark.parametrize("shim,ref,nx,ny,steps,tol_rho,tol_u", PAIRS, ids=[p[0] for p in PAIRS])
@@ -252,3 +255,21 @@ def test_checkpoint_restart_on_several_slabs(tmp_path):
     assert "at step 30" in out
     for k in ("error_pct", "mean_rho", "sum_u2"):
         assert a[k] == b[k], (k, a[k], b[k])
+
+
+def test_ghia_validation_of_the_converged_cavity(tmp_path):
+    """SURVEY.md 8f-1 / lidDrivenCavityScenario.cuh:88-157: the reference validates its cavity against the centre-line tables of
+    Ghia, Ghia & Shin (1982).  (a) The reference's OWN scenario file (129^2, Re = 100, BGK, regularized walls) on the engine, run to
+    convergence: its own host-side metric and the same metric with the 2 x 17 samples gathered on the device (lbm_sample_velocity).
+    (b) Re = 1000 with CM<2,NoAdapter> (the reference's functors and tables, constants chosen by -D).  Calibration with the CPU
+    oracle (same arithmetic): 1.32 % at Re = 100 from 60 000 steps on, 1.55 % at Re = 1000 after 120 000."""
+    res, errors, out = run_shim("ref_lid_129", tmp_path, "--steps", 60000, "--save-int", 60000, "--fast")
+    host = errors[-1][1]
+    m = re.search(r"samples gathered on the device, ([0-9.]+)%", out)
+    assert m, out[-1500:]
+    dev = float(m.group(1))
+    print(f"Ghia Re=100 BGK 129^2 after 60000 steps: reference metric {host:.4f} % (host), {dev:.4f} % (device samples)")
+    assert 1.0 < host < 1.7 and abs(host - dev) < 2e-3, (host, dev)
+    res, errors, out = run_shim("ref_ghia_re1000_cm_129", tmp_path, "--steps", 120000, "--save-int", 120000, "--fast")
+    print(f"Ghia Re=1000 CM 129^2 after 120000 steps: {errors[-1][1]:.4f} %")
+    assert 1.0 < errors[-1][1] < 2.0, errors

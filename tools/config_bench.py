@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""MLUPS of the five BASELINE.json configurations on one B200 through the public host API (cuda_lbm_b200.LBM + the
-scenario mirror), next to the reference's own CUDA solver where its binary is present (oracle/_ref/bin, built by
+"""MLUPS of the five BASELINE.json configurations on one B200 through cuda_lbm_b200.Engine and the Python scenario mirror
+(tools/pyscenarios.py), next to the reference's own CUDA solver where its binary is present (oracle/_ref/bin, built by
 oracle/build_ref.sh).  Development / reporting tool; bench.py is the contract benchmark.
 
   python tools/config_bench.py [c1 c2 c3 c4 c5] [--steps K]
@@ -17,7 +17,8 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 import cuda_lbm_b200 as L  # noqa: E402
-from cuda_lbm_b200 import scenarios as S  # noqa: E402
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import pyscenarios as S  # noqa: E402
 
 f32 = np.float32
 
@@ -28,10 +29,10 @@ def cfg(name):
     if name == "c2":
         return dict(nx=1024, ny=256, sc=S.PoiseuilleScenario(collision=L.MRT), steps=1000, ref="c2_pois_mrt_1024x256", adapter=L.ADAPTER_EXACT)
     if name == "c3":
-        return dict(nx=4096, ny=4096, sc=S.LidDrivenScenario(collision=L.CM_OPTIMAL, u_max=0.1, viscosity=0.4096), steps=200,
-                    ref=None, adapter=L.ADAPTER_EXACT)    # reference CUDA: 3613 MLUPS (profiles/r01_reference_cuda_mlups.txt); its CM warning printf makes a re-run take ~10 min
+        return dict(nx=4096, ny=4096, sc=S.LidDrivenScenario(collision=L.CM_OPTIMAL, u_max=0.1, viscosity=0.4096), steps=32,
+                    ref=None, adapter=L.ADAPTER_EXACT)    # 6 + 32 steps: inside the ~40 steps for which the reference's adapter keeps this cavity finite (tools/c3_probe.py)
     if name == "c3l":
-        return dict(nx=4096, ny=4096, sc=S.LidDrivenScenario(collision=L.CM_OPTIMAL, u_max=0.1, viscosity=0.4096), steps=200,
+        return dict(nx=4096, ny=4096, sc=S.LidDrivenScenario(collision=L.CM_OPTIMAL, u_max=0.1, viscosity=0.4096), steps=32,
                     ref=None, adapter=L.ADAPTER_LAGGED)
     if name == "c4":
         return dict(nx=32768, ny=32768, sc=S.TaylorGreenScenario(scale=256, collision=L.BGK), steps=40, ref=None, adapter=L.ADAPTER_EXACT)
@@ -49,7 +50,7 @@ def run(name, steps_override=None):
     c = cfg(name)
     nx, ny, sc = c["nx"], c["ny"], c["sc"]
     steps = steps_override or c["steps"]
-    lbm = L.LBM(nx, ny, adapter_mode=c["adapter"])
+    lbm = S.LBM(nx, ny, adapter_mode=c["adapter"])
     lbm.allocate(sc)
     if name.startswith("c4"):
         # the Init functor on the device (a 32768^2 host field would be 12.9 GB)

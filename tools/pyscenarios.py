@@ -1,4 +1,7 @@
-"""Host-side mirror of the reference's scenario layer (src/scenarios/, L4 in SURVEY.md §1).
+"""DEVELOPMENT TOOLING (used by tools/config_bench.py only) — a Python/numpy mirror of the reference's scenario layer
+(src/scenarios/, L4 in SURVEY.md §1) and of the LBM<2> driver protocol over cuda_lbm_b200.Engine.  The reference-facing host interface
+of this repository is the C++ header shim include/cuda-lbm/ (LBM<2>, ScenarioTrait); bench.py measures the BASELINE configurations
+through it (examples/main.cu).
 
 `ScenarioTrait` keeps the members of src/scenarios/scenario.cuh:22-78 (InitType / BoundaryType /
 ValidationType / CollisionOp as class attributes, viscosity / tau / omega / S / u_max, name(), init(),
@@ -11,7 +14,8 @@ import math
 
 import numpy as np
 
-from . import _capi as capi
+from cuda_lbm_b200 import _capi as capi
+from cuda_lbm_b200.solver import Engine
 
 f32 = np.float32
 
@@ -400,3 +404,100 @@ class FlowPastCylinderScenario(ScenarioTrait):
 
     def add_bodies(self, nx, ny):
         self.IBM_bodies.append(create_cylinder(self.cx, self.cy, self.r, self.num_pts))
+
+
+class LBM:
+    """Drop-in for the reference's `LBM<2>` object (see module docstring).  `Scenario` objects follow
+    cuda_lbm_b200.scenarios.ScenarioTrait, the mirror of src/scenarios/scenario.cuh:22-78."""
+
+    def __init__(self, nx, ny, device=0, quirks=capi.QK_REFERENCE, adapter_mode=capi.ADAPTER_EXACT):
+        self.NX, self.NY = nx, ny
+        self.device, self.quirks, self.adapter_mode = device, quirks, adapter_mode
+        self.timestep = 0
+        self.update_ts = 0
+        self.h_rho = np.zeros(nx * ny, np.float32)
+        self.h_u = np.zeros(2 * nx * ny, np.float32)
+        self.engine = None
+        self._pending = False
+
+    # LBM::allocate<Scenario>()  lbm.cuh:92-125
+    def allocate(self, S):
+        self.engine = Engine(self.NX, self.NY, collision=S.collision, viscosity=S.viscosity, S=S.S, periodic=S.periodic,
+                             u_max=S.u_max, force=S.body_force(self.NX, self.NY), quirks=self.quirks,
+                             adapter_mode=self.adapter_mode, device=self.device)
+        S.IBM_bodies.clear()
+        S.add_bodies(self.NX, self.NY)
+        for body in S.IBM_bodies:
+            self.engine.add_body(body)
+
+    # LBM::init<Scenario>()  init.cuh:45-86
+    def init(self, S):
+        init = S.init(self.NX, self.NY)
+        rho, u = init()
+        boundary = S.boundary(self.NX, self.NY)
+        yy, xx = np.meshgrid(np.arange(self.NY), np.arange(self.NX), indexing="ij")
+        self.engine.set_flags(boundary(xx, yy))
+        self.engine.init_fields(rho, u)
+        self.timestep = 0
+        self._pending = False
+
+    def _close_step(self, macroscopics=False):
+        if self._pending:
+            self.engine.step(1, macroscopics=macroscopics)
+            self._pending = False
+
+    def increase_ts(self, S=None):
+        self._close_step()
+        self.timestep += 1
+        if S is not None:
+            S.update_ts(self.timestep)
+
+    # the reference's per-kernel host methods (lbm.cuh:345-377): recorded, executed fused
+    def stream(self): pass
+    def swap_buffers(self): pass
+    def apply_boundaries(self, S=None): pass
+    def uncorrected_macroscopics(self): pass
+    def reset_forces(self, S=None): pass
+    def ibm_step(self): pass
+    def correct_macroscopics(self): pass
+    def compute_equilibrium(self): pass
+
+    def collide(self, op=None):
+        self._pending = True
+
+    def run(self, nsteps, S=None):
+        """nsteps iterations of the main.cu loop body without the per-call overhead."""
+        self._close_step()
+        if nsteps > 0:
+            self.engine.step(nsteps - 1)
+            self.timestep += nsteps
+            self._pending = True
+            if S is not None:
+                S.update_ts(self.timestep)
+
+    # LBM::update_macroscopics()  lbm.cuh:148-154
+    def update_macroscopics(self):
+        if self._pending:
+            self._close_step(macroscopics=True)
+        rho, u = self.engine.macroscopics()
+        self.h_rho[:] = rho.reshape(-1)
+        self.h_u[:] = u.reshape(-1)
+        self.update_ts = self.timestep
+
+    def get_rho(self):
+        return self.h_rho
+
+    def get_u(self):
+        return self.h_u
+
+    # LBM::compute_error<Scenario>()  lbm.cuh:163-171
+    def compute_error(self, S):
+        if S.has_analytical_solution:
+            return S.compute_error(self)
+        print("Scenario does not provide verification/validation.")
+        return 0.0
+
+    def free(self):
+        if self.engine is not None:
+            self.engine.close()
+            self.engine = None
