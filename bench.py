@@ -163,9 +163,11 @@ def reference_cuda_mlups(binary, steps, timeout=600):
 CONFIGS = {
     "c1": ("ex_c1_tg_256", "c1_tg_bgk_256", 256, 256, "BGK", 64, 4000, 200, "Taylor-Green 256x256 BGK (configs[0])"),
     "c2": ("ex_c2_pois_1024x256", "c2_pois_mrt_1024x256", 1024, 256, "MRT", 64, 4000, 200, "Poiseuille 1024x256 MRT, body force, bounce-back walls (configs[1])"),
-    "c3": ("ex_c3_lid_4096", "c3_lid_cmopt_4096", 4096, 4096, "CM<OptimalAdapter> (exact grid means)", 16, 48, 40,
+    # 18 + 17 steps: the reference's adapter keeps this cavity physical for ~40 steps (tools/c3_probe.py, profiles/r02_c3_probe.txt); the
+    # warm-up covers module load and the capture of the 16-step CUDA graph that the timed steps replay (same parity)
+    "c3": ("ex_c3_lid_4096", "c3_lid_cmopt_4096", 4096, 4096, "CM<OptimalAdapter> (exact grid means)", 18, 17, 36,
            "lid-driven cavity 4096x4096 CM<OptimalAdapter> (configs[2]); run inside the window in which the reference's adapter keeps the field finite"),
-    "c3_lagged": ("ex_c3_lid_4096", None, 4096, 4096, "CM<OptimalAdapter> (grid means of the previous step)", 16, 48, 0,
+    "c3_lagged": ("ex_c3_lid_4096", None, 4096, 4096, "CM<OptimalAdapter> (grid means of the previous step)", 18, 17, 0,
                   "configs[2] with LBM_ADAPTER_LAGGED (72 B/cell; deviation from the exact mode: tests/test_reference_fullsize_gpu.py)"),
     "c5": ("ex_c5_cyl_8192x2048", "c5_cyl_ibm_mrt_8192x2048", 8192, 2048, "MRT + IBM (256 markers)", 32, 400, 60,
            "flow past cylinder 8192x2048 MRT, IBM direct forcing (configs[4])"),
@@ -194,7 +196,7 @@ def run_config(name, peak):
     cells = nx * ny
     out = {"name": name, "workload": what, "nx": nx, "ny": ny, "collision": op, "warmup_steps": warm, "steps": steps,
            "mlups": mlups, "ms_per_step": float(res["ms_per_step"]),
-           "finite": bool(mass == mass and abs(mass) < 1e30 and float(res["sum_u2"]) == float(res["sum_u2"])), "mass_per_node": mass,
+           "physical": bool(abs(mass - 1.0) < 0.05 and float(res["sum_u2"]) == float(res["sum_u2"])), "mass_per_node": mass,
            "api": "examples/main.cu over the LBM<2> / ScenarioTrait header shim (include/cuda-lbm), LBM::run<Scenario>(n)"}
     # the HBM roofline applies where the populations (36 B/cell) do not fit the 126 MB L2
     out["roofline_frac"] = (BYTES_PER_UPDATE * mlups * 1e6 / 1e9 / peak) if 36.0 * cells > 4 * 126e6 else None

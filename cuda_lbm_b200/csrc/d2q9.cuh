@@ -51,10 +51,12 @@ struct Params {
     const float* avg;       // 3 floats: grid means of rho, rho|u|, |Pi| (OptimalAdapter)
     float* partials;        // per-block partial sums (3 per block) or nullptr
     float* rho_out; float2* u_out;     // macroscopic output of this step (nullptr = none)
-    // segments: 128 consecutive cells of one row.  segmask[yl*nsx + sx] != 0 marks a "general" segment (boundary flags,
-    // IBM nodes, per-node force, non-periodic domain edge); the vectorised kernel skips those and the scalar kernel
-    // processes exactly the ones listed in gen_list.
+    // segments: 128 consecutive cells of one row.  segmask[yl*nsx + sx]: 0 = every cell is plain stream + collide (vectorised
+    // kernels), 1 = every cell takes the general path (boundary flags, IBM nodes, per-node force, non-periodic domain edge), 2 = mixed:
+    // the vectorised kernels skip exactly the general cells.  The general (scalar) kernel is launched over the segments listed in
+    // gen_list (type 1) and over the cells listed in gen_cells (the general cells of type-2 segments, local node ids).
     const uint8_t* segmask; int nsx; const int* gen_list;
+    const long long* gen_cells; long long gen_cell_count;
     // direct y-slab coupling over NVLink peer memory: [0] = the lower neighbour's top edge row, [1] = the upper neighbour's
     // bottom edge row, addressed as peer[s] + plane * peer_plane[s] + peer_off[s] + x.  nullptr = use this slab's ghost rows.
     float* peer[2]; long long peer_plane[2]; long long peer_off[2];

@@ -85,16 +85,14 @@ struct lbm_handle {
     std::vector<int> ibm_rows;                   // distinct rows of this slab's active stencil nodes (peer-coverage check)
     // general-path segments (kernels.cuh): mask per 128-cell segment + compact list, rebuilt lazily
     uint8_t* segmask = nullptr; int* gen_list = nullptr; int gen_count = 0; int nsx = 0; bool segs_dirty = true;
+    long long* gen_cells = nullptr; long long gen_cell_count = 0, gen_cell_cap = 0;      // general cells of the mixed segments (local node ids)
     // adapter
     float* partials = nullptr; long long n_partials = 0; double* stage = nullptr; double* sums = nullptr; float* avg = nullptr; int avg_for_ts = -1; int pre_for_ts = -1;
     // macroscopics
     float* rho_out = nullptr; float2* u_out = nullptr; int macros_ts = -1;
     double* mass_acc = nullptr;
     double* val_stage = nullptr; long long val_stage_n = 0;      // validation reductions (lbm_*_error_sums, lbm_row_mean_velocity)
-    // odd phase through TMA (step_tma_kernel): a 3-D tensor map (x, row, plane) over the population allocation
-    alignas(64) CUtensorMap tmap{};
-    bool tma_ok = false;            // tensor map encoded, nx % 128 == 0, not disabled by LBM_B200_TMA=0
-    int tma_grid[4] = {0, 0, 0, 0}; // persistent grid per collision operator: SMs x resident blocks
+    bool odd_interleaved = true;    // odd phase with step_odd_kernel where rows are whole segments (LBM_B200_ODD=0: the shuffle-based kernel everywhere)
     int timestep = 0;
     long long launches = 0;
     long long bytes = 0;
@@ -154,7 +152,7 @@ static Params make_params(lbm_handle* h, int t) {
     p.nbr_nodes = h->nbr_nodes; p.nbr_g = h->nbr_g; p.nbr_count = h->nbr_count;
     p.ibm_nodes = h->ibm_nodes; p.ibm_force = h->ibm_force; p.ibm_count = h->ibm_count;
     p.avg = h->avg; p.partials = nullptr; p.rho_out = nullptr; p.u_out = nullptr;
-    p.segmask = nullptr; p.nsx = h->nsx; p.gen_list = nullptr; p.plane = (long long)h->plane;
+    p.segmask = nullptr; p.nsx = h->nsx; p.gen_list = nullptr; p.gen_cells = nullptr; p.gen_cell_count = 0; p.plane = (long long)h->plane;
     for (int sd = 0; sd < 2; sd++) { p.peer[sd] = h->peer[sd].attached ? h->peer[sd].base : nullptr; p.peer_plane[sd] = h->peer[sd].plane; p.peer_off[sd] = h->peer[sd].off; }
     return p;
 }
@@ -165,7 +163,7 @@ static Params make_params(lbm_handle* h, int t) {
 // loaded up front instead, once per device, before any handle exists.
 template <typename K> static void preload(K kernel) { cudaFuncAttributes a; cudaFuncGetAttributes(&a, kernel); }
 template <int COLL> static void preload_coll() {
-    preload(step_vec_kernel<COLL, false>); preload(step_vec_kernel<COLL, true>); preload(step_tma_kernel<COLL>);
+    preload(step_vec_kernel<COLL, false>); preload(step_vec_kernel<COLL, true>); preload(step_odd_kernel<COLL>);
     preload(step_kernel<COLL, false, false>); preload(step_kernel<COLL, false, true>);
     preload(step_kernel<COLL, true, false>); preload(step_kernel<COLL, true, true>);
 }
@@ -188,35 +186,6 @@ static void preload_kernels(int device) {
 }
 
 static dim3 grid_of(const lbm_handle* h) { return dim3((h->cfg.nx + BX - 1) / BX, h->nyl); }
-
-// Tensor map of the population planes for the TMA odd-phase kernel: dims (x = nx, row = nyl + 2, plane = nplanes), 128 x 1 x 1 boxes,
-// no swizzle, zero fill.  cuTensorMapEncodeTiled comes from the driver through the runtime's entry-point query, so the library keeps
-// linking against cudart only.  Any failure simply leaves the shuffle-based kernel in charge of the odd phase.
-template <int COLL> static int tma_resident_blocks() {
-    int nb = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, step_tma_kernel<COLL>, BX, TMA_SMEM_BYTES) != cudaSuccess) { cudaGetLastError(); return 0; }
-    return nb;
-}
-static void setup_tma(lbm_handle* h) {
-    h->tma_ok = false;
-    if (const char* v = getenv("LBM_B200_TMA")) if (v[0] == '0') return;
-    if (h->cfg.nx % SEG != 0) return;
-    typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
-                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-    void* fn = nullptr;
-    cudaDriverEntryPointQueryResult qr;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess || !fn) { cudaGetLastError(); return; }
-    const cuuint64_t dims[3] = {(cuuint64_t)h->cfg.nx, (cuuint64_t)(h->nyl + 2), (cuuint64_t)h->nplanes};
-    const cuuint64_t strides[2] = {(cuuint64_t)h->cfg.nx * 4, (cuuint64_t)h->plane * 4};
-    const cuuint32_t box[3] = {(cuuint32_t)SEG, 1, 1}, estr[3] = {1, 1, 1};
-    if (((encode_fn)fn)(&h->tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, h->pop, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return;
-    cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, h->cfg.device) != cudaSuccess) { cudaGetLastError(); return; }
-    const int per_sm[4] = {tma_resident_blocks<C_BGK>(), tma_resident_blocks<C_MRT>(), tma_resident_blocks<C_CM>(), tma_resident_blocks<C_CMOPT>()};
-    for (int c = 0; c < 4; c++) { if (per_sm[c] < 1) return; h->tma_grid[c] = per_sm[c] * prop.multiProcessorCount; }
-    h->tma_ok = true;
-}
 
 extern "C" const char* lbm_last_error(void) { return g_err.c_str(); }
 
@@ -241,7 +210,7 @@ extern "C" int lbm_destroy(lbm_handle* h) {
     for (auto& m : h->mapped) if (m.ipc_base) cudaIpcCloseMemHandle(m.ipc_base);
     void* ptrs[] = {h->d_net, h->sync_timeout, h->pop, h->flags, h->force_plane, h->ring, h->nbr_nodes, h->nbr_src, h->nbr_g, h->d_pts, h->ibm_nodes,
                     h->sten_idx, h->sten_w, h->csr_row, h->csr_k, h->csr_w, h->ibm_rho, h->ibm_uprev, h->ibm_lagF, h->ibm_force, h->ibm_mail_idx, h->d_utarget,
-                    h->partials, h->stage, h->sums, h->avg, h->rho_out, h->u_out, h->mass_acc, h->segmask, h->gen_list, h->val_stage};
+                    h->partials, h->stage, h->sums, h->avg, h->rho_out, h->u_out, h->mass_acc, h->segmask, h->gen_list, h->gen_cells, h->val_stage};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     for (auto& g : h->graph) if (g.exec) cudaGraphExecDestroy(g.exec);
@@ -318,7 +287,7 @@ extern "C" int lbm_create(const lbm_config* cfg, lbm_handle** out) {
     h->ibm_mail = h->mail_nodes ? h->pop + pop_floats + TAIL_FIXED_BYTES / 4 : nullptr;
     cudaMemsetAsync(h->d_net, 0, sizeof(SlabNet), h->stream);
     cudaMemsetAsync(h->ring, 0, (size_t)2 * h->perim * Q * sizeof(float), h->stream);
-    setup_tma(h);
+    if (const char* v = getenv("LBM_B200_ODD")) h->odd_interleaved = v[0] != '0';
     float one[3] = {1.f, 1.f, 1.f};
     cudaMemcpyAsync(h->avg, one, sizeof(one), cudaMemcpyHostToDevice, h->stream);
     cudaStreamSynchronize(h->stream);

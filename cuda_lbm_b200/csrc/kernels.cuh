@@ -1,6 +1,5 @@
 // kernels.cuh — the __global__ kernels of the engine (see d2q9.cuh for the per-cell functions).
 #pragma once
-#include <cuda.h>           // CUtensorMap (the TMA odd-phase kernel)
 #include "d2q9.cuh"
 
 namespace lbm {
@@ -39,6 +38,38 @@ __device__ __forceinline__ void node_pre_collision(const Params& p, int x, int y
     if (s.Fx != 0.0f || s.Fy != 0.0f) { s.ux = __fmaf_rn(s.Fx, h, s.m.ux); s.uy = __fmaf_rn(s.Fy, h, s.m.uy); }
 }
 
+// Which kernel owns a cell?  The vectorised kernels do stream + collide only: a cell with a boundary flag or under a marker stencil
+// (flag byte != 0) or on a non-periodic domain edge (undelivered slots, edge ring) belongs to the general (scalar) kernel.
+// Segments (128 cells of a row) are classified once (build_segmask_kernel): SEG_VEC no such cell, SEG_GENERAL all of them (or a
+// per-node force plane: everything), SEG_MIXED some — the vectorised kernels then skip exactly those cells, which the general
+// kernel takes from a per-cell list.  Under the AA pattern a cell reads exactly the slots it overwrites, so any split is race-free.
+constexpr uint8_t SEG_VEC = 0, SEG_GENERAL = 1, SEG_MIXED = 2;
+__device__ __forceinline__ bool cell_is_general(const Params& p, int x, int yl) {
+    if (p.flags && p.flags[(long long)yl * p.nx + x]) return true;
+    if (!p.px && (x == 0 || x == p.nx - 1)) return true;
+    const int yg = p.y0 + yl;
+    return !p.py && (yg == 0 || yg == p.ny - 1);
+}
+// the general kernels' three launch shapes: whole slab (grid = segments x rows), listed segments, listed cells
+__device__ __forceinline__ bool general_cell_of_thread(const Params& p, int& x, int& yl) {
+    if (p.gen_cells) {
+        const long long i = (long long)blockIdx.x * BX + threadIdx.x;
+        if (i >= p.gen_cell_count) return false;
+        const long long ln = p.gen_cells[i];
+        yl = (int)(ln / p.nx); x = (int)(ln - (long long)yl * p.nx);
+        return true;
+    }
+    if (p.gen_list) {
+        const int seg = p.gen_list[blockIdx.x];
+        yl = seg / p.nsx;
+        x = (seg - yl * p.nsx) * SEG + threadIdx.x;
+    } else {
+        x = blockIdx.x * BX + threadIdx.x;
+        yl = blockIdx.y;
+    }
+    return x < p.nx;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -67,17 +98,10 @@ __device__ __forceinline__ void block_partials(float a, float b, float c, float*
 // vectorised kernel below covering everything else.
 template <int COLL, bool ODD, bool GENERAL>
 __global__ void __launch_bounds__(BX) step_kernel(const Params p) {
-    int x, yl;
-    if (p.gen_list) {
-        const int seg = p.gen_list[blockIdx.x];
-        yl = seg / p.nsx;
-        x = (seg - yl * p.nsx) * SEG + threadIdx.x;
-    } else {
-        x = blockIdx.x * BX + threadIdx.x;
-        yl = blockIdx.y;
-    }
+    int x = 0, yl = 0;
+    const bool on = general_cell_of_thread(p, x, yl);
     float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-    if (x < p.nx) {
+    if (on) {
         NodeState s;
         node_pre_collision<ODD, GENERAL>(p, x, yl, s);
         if (p.rho_out) {
@@ -164,6 +188,25 @@ __device__ __forceinline__ void st4(float* p, float a, float b, float c, float d
 #endif
 }
 
+// SEG_MIXED segments: bit k set = cell x0 + k of this thread belongs to the general kernel
+__device__ __forceinline__ unsigned skip_mask4(const Params& p, int x0, int yl) {
+    unsigned m = 0;
+    if (p.flags) {
+        const uchar4 f = *reinterpret_cast<const uchar4*>(p.flags + (long long)yl * p.nx + x0);
+        m = (f.x ? 1u : 0u) | (f.y ? 2u : 0u) | (f.z ? 4u : 0u) | (f.w ? 8u : 0u);
+    }
+    if (!p.px) { if (x0 == 0) m |= 1u; if (x0 + 4 == p.nx) m |= 8u; }
+    return m;
+}
+__device__ __forceinline__ void st4_masked(float* ptr, float a, float b, float c, float d, unsigned skip) {
+    if (skip == 0) { st4(ptr, a, b, c, d); return; }
+    if (!(skip & 1u)) ptr[0] = a;
+    if (!(skip & 2u)) ptr[1] = b;
+    if (!(skip & 4u)) ptr[2] = c;
+    if (!(skip & 8u)) ptr[3] = d;
+}
+__device__ __forceinline__ V2 zero_lanes(V2 v, bool z0, bool z1) { V2 r; r.a = make_float2(z0 ? 0.0f : v.a.x, z1 ? 0.0f : v.a.y); return r; }
+
 // f[0..3] of cells x0..x0+3 go to x0+1 .. x0+4
 __device__ __forceinline__ void store_to_right(float* r, int x0, int xr, bool hasL, bool hasR, bool act, const float f[4]) {
     const float l = __shfl_up_sync(FULL, f[3], 1);
@@ -184,6 +227,7 @@ __device__ __forceinline__ void store_to_left(float* r, int x0, int xl, bool has
 // Where a thread of the vectorised kernels works: cells x0 .. x0+3 of row yl, and how it reaches rows y-1 / y+1.
 struct VecCtx {
     int yl, x0, xl, xr, gen;
+    unsigned skip;              // SEG_MIXED: cells of this thread the general kernel owns
     bool act, hasL, hasR;
     long long r0;
     float *bm, *bp;             // rows y-1 / y+1 of plane k start at bm + k*sm / bp + k*sp: this slab, its ghost rows, or (peer-mapped) the neighbour slab
@@ -200,9 +244,11 @@ __device__ __forceinline__ bool vec_setup(const Params& p, VecCtx& c) {
     c.act = xv_raw < nv;
     const int xv = c.act ? xv_raw : nv - 1;           // idle lanes of the last warp shadow a valid cell (loads only)
     bool warp_on = (xv_raw & ~31) < nv;               // warp-uniform: one warp = one 128-cell segment
-    if (warp_on && p.segmask) warp_on = p.segmask[(long long)c.yl * p.nsx + (xv_raw >> 5)] == 0;
+    uint8_t segtype = SEG_VEC;
+    if (warp_on && p.segmask) { segtype = p.segmask[(long long)c.yl * p.nsx + (xv_raw >> 5)]; warp_on = segtype != SEG_GENERAL; }
     if (!warp_on) return false;
     c.x0 = xv << 2;
+    c.skip = segtype == SEG_MIXED ? skip_mask4(p, c.x0, c.yl) : 0u;
     c.r0 = rowoff(p, c.yl);
     c.gen = p.t & 1;
     // neighbours inside the warp exchange the boundary element; a row starts at lane 0 (blockDim.x % 32 == 0)
@@ -275,10 +321,14 @@ __global__ void __launch_bounds__(BX, vec_min_blocks(COLL, ODD)) step_vec_kernel
     bool act = xv_raw < nv;
     const int xv = act ? xv_raw : nv - 1;             // idle lanes of the last warp shadow a valid cell (loads only)
     bool warp_on = (xv_raw & ~31) < nv;               // warp-uniform: one warp = one 128-cell segment
-    if (warp_on && p.segmask) warp_on = p.segmask[(long long)yl * p.nsx + (xv_raw >> 5)] == 0;
+    uint8_t segtype = SEG_VEC;
+    if (warp_on && p.segmask) { segtype = p.segmask[(long long)yl * p.nsx + (xv_raw >> 5)]; warp_on = segtype != SEG_GENERAL; }
     float s0 = 0.f, s1 = 0.f, s2 = 0.f;
     if (warp_on) {
         const int x0 = xv << 2;
+        // cells of this thread the general kernel owns (even phase only: the host never hands SEG_MIXED segments to the odd branch of
+        // this kernel — step_odd_kernel below is the odd phase wherever segments can be mixed)
+        const unsigned skip = (!ODD && segtype == SEG_MIXED) ? skip_mask4(p, x0, yl) : 0u;
         const long long r0 = rowoff(p, yl);
         const int gen = p.t & 1;
         // CM<2,OptimalAdapter>: the three grid means come from memory (the previous launch wrote them).  Their loads are issued
@@ -362,23 +412,24 @@ __global__ void __launch_bounds__(BX, vec_min_blocks(COLL, ODD)) step_vec_kernel
             else if (COLL == C_CM) collide_cm_v<false>(rx, g[hf], ux, uy, forced, Fx, Fy, splat<V2>(1.0f));
             else {
                 const V2 jm = jmag_v(ux, uy, m.rho), pm = pi_norm_v(m);
-                acc0 = acc0 + m.rho; acc1 = acc1 + jm; acc2 = acc2 + pm;
+                const bool z0 = (skip >> (2 * hf)) & 1u, z1 = (skip >> (2 * hf + 1)) & 1u;        // their sums come from the general kernel
+                acc0 = acc0 + zero_lanes(m.rho, z0, z1); acc1 = acc1 + zero_lanes(jm, z0, z1); acc2 = acc2 + zero_lanes(pm, z0, z1);
                 collide_cm_v<true>(rx, g[hf], ux, uy, forced, Fx, Fy, optimal_rate_v(m.rho, jm, pm, av));
             }
         }
         if (COLL == C_CMOPT && act) { s0 = hsum(acc0); s1 = hsum(acc1); s2 = hsum(acc2); }
         if (p.rho_out && act) {
             const long long ln = (long long)yl * p.nx + x0;
-            st4(p.rho_out + ln, rho4[0].x, rho4[0].y, rho4[1].x, rho4[1].y);
+            st4_masked(p.rho_out + ln, rho4[0].x, rho4[0].y, rho4[1].x, rho4[1].y, skip);
             float* uo = reinterpret_cast<float*>(p.u_out + ln);
-            st4(uo, ux4[0].x, uy4[0].x, ux4[0].y, uy4[0].y);
-            st4(uo + 4, ux4[1].x, uy4[1].x, ux4[1].y, uy4[1].y);
+            st4_masked(uo, ux4[0].x, uy4[0].x, ux4[0].y, uy4[0].y, (skip & 1u ? 3u : 0u) | (skip & 2u ? 12u : 0u));
+            st4_masked(uo + 4, ux4[1].x, uy4[1].x, ux4[1].y, uy4[1].y, (skip & 4u ? 3u : 0u) | (skip & 8u ? 12u : 0u));
         }
-        if (act) st4(p.A0[gen] + r0 + x0, g[0][0].a.x, g[0][0].a.y, g[1][0].a.x, g[1][0].a.y);
+        if (act) st4_masked(p.A0[gen] + r0 + x0, g[0][0].a.x, g[0][0].a.y, g[1][0].a.x, g[1][0].a.y, skip);
         if (!ODD) {
             if (act) {
 #pragma unroll
-                for (int q = 1; q < Q; q++) st4(p.A[opp(q)] + r0 + x0, g[0][q].a.x, g[0][q].a.y, g[1][q].a.x, g[1][q].a.y);
+                for (int q = 1; q < Q; q++) st4_masked(p.A[opp(q)] + r0 + x0, g[0][q].a.x, g[0][q].a.y, g[1][q].a.x, g[1][q].a.y, skip);
             }
         } else {
 #pragma unroll
@@ -395,143 +446,75 @@ __global__ void __launch_bounds__(BX, vec_min_blocks(COLL, ODD)) step_vec_kernel
     if (COLL == C_CMOPT && p.partials) block_partials(s0, s1, s2, p.partials + 3 * ((long long)blockIdx.y * gridDim.x + blockIdx.x));
 }
 
-// ------------------------------------------------------------------ odd (neighbour) phase through the Tensor Memory Accelerator
-// The odd AA phase reads A[opp q][x - c_q] and writes A[q][x + c_q]: six of the nine slot planes are shifted by one cell in x, which
-// costs the kernel above ~280 of its ~1000 warp instructions per 128 cells (aligned float4 + lane shuffles + predicated scalar
-// accesses for the element that crosses a 16-byte boundary; ncu: profiles/r02_ncu_cmopt_before.md) and 36 staging registers.  TMA
-// tile copies take ELEMENT coordinates, so here the shift is part of the copy: per 128-cell segment one lane issues nine
-// cp.async.bulk.tensor loads of a 128 x 1 x 1 box at (x0 - c_x, y - c_y, opp q) into shared memory, every lane then reads its four
-// cells of each plane with one aligned LDS.128, collides, writes the results back in place, and nine tensor stores at
-// (x0 + c_x, y + c_y, q) put them where the next (even) step reads them.  Each WARP owns its segments, its shared-memory stages
-// and its mbarriers: no block-wide synchronisation.  Warps are persistent and prefetch the next segment's nine boxes while they
-// collide the current one, so the memory latency is covered by the copy engine instead of by occupancy.
-// Out-of-range box elements (x = -1 or nx on a row end) are zero-filled on load and clipped on store: the one element per row end
-// that wraps around periodically is loaded / stored by the lane that owns the cell, as a scalar access.
-#ifndef LBM_TMA_STAGES
-#define LBM_TMA_STAGES 2
+// ------------------------------------------------------------------ odd (neighbour) phase, lane-interleaved cells
+// The odd AA phase reads A[opp q][x - c_q] and writes A[q][x + c_q]: six of the nine slot planes are shifted by one cell in x.  The
+// kernel above keeps 128-bit accesses for them (aligned float4 + lane shuffles + predicated scalar accesses for the element that
+// crosses a 16-byte boundary), which ncu shows to cost ~280 of its ~1000 warp instructions per 128 cells, 76 of them register moves
+// that re-pair the shifted elements for the packed fp32 instructions (profiles/r02_ncu_cm_opt_odd_before.md), and 36 staging registers.
+// (TMA cannot take the shift either: a tensor-map box must start on a 16-byte boundary in global memory — tools/tma_probe.cu,
+// profiles/r02_tma_probe.txt.)  Here a warp still owns one 128-cell segment, but lane l works on cells x0 + l, l + 32, l + 64, l + 96:
+// every access is a 32-bit load / store that the warp coalesces into one 128-byte request whatever the shift, the two cells of a
+// packed pair are loaded straight into a register pair, and there is nothing to shuffle, predicate or re-pair.  Same per-cell
+// arithmetic as every other kernel (bit-identical results).  Needs rows made of whole segments (nx % 128 == 0).
+#ifndef LBM_ODD_MIN_BLOCKS
+#define LBM_ODD_MIN_BLOCKS 5
 #endif
-#ifndef LBM_TMA_MIN_BLOCKS
-#define LBM_TMA_MIN_BLOCKS 4
+#ifndef LBM_ODD_MIN_BLOCKS_OPT
+#define LBM_ODD_MIN_BLOCKS_OPT 4
 #endif
-constexpr int TMA_STAGES = LBM_TMA_STAGES;
-constexpr int TMA_WARPS = BX / 32;
-constexpr int TMA_STAGE_FLOATS = Q * SEG;                                 // nine 128-cell boxes = 4608 B
-constexpr int TMA_SMEM_BYTES = TMA_WARPS * TMA_STAGES * TMA_STAGE_FLOATS * 4 + TMA_WARPS * TMA_STAGES * 8;
-
-__device__ __forceinline__ unsigned smem_u32(const void* ptr) { return (unsigned)__cvta_generic_to_shared(ptr); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "LBM_MBAR_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra LBM_MBAR_DONE;\n"
-        "bra LBM_MBAR_WAIT;\n"
-        "LBM_MBAR_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_box(float* dst, const void* tmap, unsigned long long* bar, int c0, int c1, int c2) {
-    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-                 ::"r"(smem_u32(dst)), "l"((unsigned long long)tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-__device__ __forceinline__ void tma_store_box(const void* tmap, const float* src, int c0, int c1, int c2) {
-    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
-                 ::"l"((unsigned long long)tmap), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void tma_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-// what the TMA kernel needs beyond Params: the rows it covers and where the two rest-population planes sit in the tensor
-struct TmaArgs {
-    int row_begin, row_end;     // local rows [row_begin, row_end): the slab without the edge rows that pull from a peer-mapped neighbour
-    int rest_plane[2];          // tensor plane index of A0[0] / A0[1]
-    float* partials;            // CM<2,OptimalAdapter>, lagged: one (rho, rho|u|, |Pi|) triple per block of THIS launch
-};
-
 template <int COLL>
-__global__ void __launch_bounds__(BX, LBM_TMA_MIN_BLOCKS) step_tma_kernel(const Params p, const __grid_constant__ CUtensorMap tmap, const TmaArgs a) {
-    extern __shared__ __align__(128) unsigned char tma_smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* wbuf = reinterpret_cast<float*>(tma_smem) + warp * (TMA_STAGES * TMA_STAGE_FLOATS);
-    unsigned long long* bars = reinterpret_cast<unsigned long long*>(tma_smem + TMA_WARPS * TMA_STAGES * TMA_STAGE_FLOATS * 4) + warp * TMA_STAGES;
-    if (lane == 0) {
-#pragma unroll
-        for (int st = 0; st < TMA_STAGES; st++) mbar_init(&bars[st], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncwarp();
-    float avg_raw[3] = {1.f, 1.f, 1.f};
-    if (COLL == C_CMOPT) { avg_raw[0] = __ldg(p.avg); avg_raw[1] = __ldg(p.avg + 1); avg_raw[2] = __ldg(p.avg + 2); }
-    const int gen = p.t & 1;
-    const int nsx = p.nsx;                                      // nx % 128 == 0 here: every segment is full
-    const int nseg = (a.row_end - a.row_begin) * nsx;
-    const int stride = gridDim.x * TMA_WARPS;
-    auto valid_from = [&](int sg) {                              // first segment >= sg (stepping by stride) the vectorised path owns
-        if (p.segmask)
-            while (sg < nseg && p.segmask[(long long)a.row_begin * nsx + sg] != 0) sg += stride;
-        return sg;
-    };
-    auto issue_loads = [&](int sg, int st) {                     // lane 0: nine boxes of segment sg into stage st
-        const int yl = a.row_begin + sg / nsx, x0 = (sg % nsx) * SEG;
-        float* dst = wbuf + st * TMA_STAGE_FLOATS;
-        mbar_expect_tx(&bars[st], TMA_STAGE_FLOATS * 4);
-        tma_load_box(dst, &tmap, &bars[st], x0, yl + 1, a.rest_plane[gen]);
-#pragma unroll
-        for (int q = 1; q < Q; q++) {
-            int ys = yl - cy(q);                                 // g_q(x) = A[opp q][x - c_q]
-            if (p.wrap_y) { if (ys < 0) ys += p.nyl; else if (ys >= p.nyl) ys -= p.nyl; }
-            tma_load_box(dst + q * SEG, &tmap, &bars[st], x0 - cx(q), ys + 1, opp(q));
-        }
-    };
-    const Relax rx = relax_of(p);
-    const bool forced = p.fx != 0.0f || p.fy != 0.0f;
-    const V2 Fx = splat<V2>(p.fx), Fy = splat<V2>(p.fy);
-    AdapterAvg av{};
-    if (COLL == C_CMOPT) { av.inv_rho = 1.0f / avg_raw[0]; av.inv_j = 1.0f / avg_raw[1]; av.inv_pi = 1.0f / avg_raw[2]; }
-    V2 acc0 = splat<V2>(0.f), acc1 = acc0, acc2 = acc0;
-
-    int sg = valid_from(blockIdx.x * TMA_WARPS + warp);
-    int st = 0;
-    unsigned phase = 0;                                         // bit st = parity the next wait on stage st expects
-    if (sg < nseg && lane == 0) issue_loads(sg, 0);
-    while (sg < nseg) {
-        const int nxt = valid_from(sg + stride);
-        if (nxt < nseg && lane == 0) {
-            tma_wait_read_all();                                // the stores that read the other stage (previous segment) are through with it
-            issue_loads(nxt, (st + 1) % TMA_STAGES);
-        }
-        const int yl = a.row_begin + sg / nsx, x0 = (sg % nsx) * SEG + 4 * lane;
-        float* buf = wbuf + st * TMA_STAGE_FLOATS + 4 * lane;
+__global__ void __launch_bounds__(BX, COLL == 3 ? LBM_ODD_MIN_BLOCKS_OPT : LBM_ODD_MIN_BLOCKS) step_odd_kernel(const Params p) {
+    const int lane = threadIdx.x & 31;
+    const int sx = blockIdx.x * (BX / 32) + (threadIdx.x >> 5);       // segment of this warp within the row
+    const int yl = blockIdx.y;
+    bool warp_on = sx < p.nsx;
+    uint8_t segtype = SEG_VEC;
+    if (warp_on && p.segmask) { segtype = p.segmask[(long long)yl * p.nsx + sx]; warp_on = segtype != SEG_GENERAL; }
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    if (warp_on) {
+        float avg_raw[3] = {1.f, 1.f, 1.f};
+        if (COLL == C_CMOPT) { avg_raw[0] = __ldg(p.avg); avg_raw[1] = __ldg(p.avg + 1); avg_raw[2] = __ldg(p.avg + 2); }
+        const int x = sx * SEG + lane;                                // cells x, x + 32, x + 64, x + 96
+        const long long r0 = rowoff(p, yl);
+        const int gen = p.t & 1;
         int ym = yl - 1, yp = yl + 1;
         if (p.wrap_y) { if (ym < 0) ym += p.nyl; if (yp >= p.nyl) yp -= p.nyl; }
-        // the two elements per row that wrap around periodically in x: scalar loads, issued before the wait
-        const bool first = x0 == 0, last = x0 + 4 == p.nx;
-        float wl[3] = {0.f, 0.f, 0.f}, wr[3] = {0.f, 0.f, 0.f};
-        if (first) {        // q with c_x = +1 (1, 5, 8) pull from x = -1 -> nx - 1 of plane opp q, row y - c_y
-            wl[0] = p.A[3][rowoff(p, yl) + p.nx - 1]; wl[1] = p.A[7][rowoff(p, ym) + p.nx - 1]; wl[2] = p.A[6][rowoff(p, yp) + p.nx - 1];
+        // rows y-1 / y+1 of plane k start at bm + k*sm / bp + k*sp: this slab, its ghost rows, or (peer-mapped) the neighbour slab
+        float* bm = p.A[0] + rowoff(p, ym); long long sm = p.plane;
+        float* bp = p.A[0] + rowoff(p, yp); long long sp = p.plane;
+        if (ym < 0 && p.peer[0]) { bm = p.peer[0] + p.peer_off[0]; sm = p.peer_plane[0]; }
+        if (yp >= p.nyl && p.peer[1]) { bp = p.peer[1] + p.peer_off[1]; sp = p.peer_plane[1]; }
+        // the one element per row end that wraps around periodically (a non-periodic row end is a general cell, never computed here)
+        const int xw_lo = x == 0 ? p.nx - 1 : x - 1;                  // source column of cell x for c_x = +1, destination for c_x = -1
+        const int xw_hi = x + 97 == p.nx ? 0 : x + 97;                // source column of cell x + 96 for c_x = -1, destination for c_x = +1
+        unsigned skip = 0;                                            // SEG_MIXED: bit j = cell x + 32 j belongs to the general kernel
+        if (segtype == SEG_MIXED) {
+            if (p.flags) {
+                const uint8_t* f = p.flags + (long long)yl * p.nx + x;
+                skip = (f[0] ? 1u : 0u) | (f[32] ? 2u : 0u) | (f[64] ? 4u : 0u) | (f[96] ? 8u : 0u);
+            }
+            if (!p.px) { if (x == 0) skip |= 1u; if (x + 97 == p.nx) skip |= 8u; }
         }
-        if (last) {         // q with c_x = -1 (3, 6, 7) pull from x = nx -> 0
-            wr[0] = p.A[1][rowoff(p, yl)]; wr[1] = p.A[8][rowoff(p, ym)]; wr[2] = p.A[5][rowoff(p, yp)];
+        V2 g[2][Q];                                                   // g[h][q]: cells x + 64 h and x + 64 h + 32 in the two packed fp32 lanes
+        {
+            const float* r = p.A0[gen] + r0 + x;
+            g[0][0].a.x = r[0]; g[0][0].a.y = r[32]; g[1][0].a.x = r[64]; g[1][0].a.y = r[96];
         }
-        mbar_wait(&bars[st], (phase >> st) & 1u);
-        phase ^= 1u << st;
-        V2 g[2][Q];
 #pragma unroll
-        for (int q = 0; q < Q; q++) {
-            const float4 v = *reinterpret_cast<const float4*>(buf + q * SEG);
-            g[0][q].a = make_float2(v.x, v.y); g[1][q].a = make_float2(v.z, v.w);
+        for (int q = 1; q < Q; q++) {
+            // g_q(x) = A[opp q][x - c_q]: source row y - c_y, source column x - c_x
+            const float* r = cy(q) > 0 ? bm + opp(q) * sm : (cy(q) < 0 ? bp + opp(q) * sp : p.A[opp(q)] + r0);
+            if (cx(q) > 0) { g[0][q].a.x = r[xw_lo]; g[0][q].a.y = r[x + 31]; g[1][q].a.x = r[x + 63]; g[1][q].a.y = r[x + 95]; }
+            else if (cx(q) < 0) { g[0][q].a.x = r[x + 1]; g[0][q].a.y = r[x + 33]; g[1][q].a.x = r[x + 65]; g[1][q].a.y = r[xw_hi]; }
+            else { g[0][q].a.x = r[x]; g[0][q].a.y = r[x + 32]; g[1][q].a.x = r[x + 64]; g[1][q].a.y = r[x + 96]; }
         }
-        if (first) { g[0][1].a.x = wl[0]; g[0][5].a.x = wl[1]; g[0][8].a.x = wl[2]; }
-        if (last) { g[1][3].a.y = wr[0]; g[1][6].a.y = wr[1]; g[1][7].a.y = wr[2]; }
         float2 rho4[2], ux4[2], uy4[2];
+        AdapterAvg av{};
+        if (COLL == C_CMOPT) { av.inv_rho = 1.0f / avg_raw[0]; av.inv_j = 1.0f / avg_raw[1]; av.inv_pi = 1.0f / avg_raw[2]; }
+        const Relax rx = relax_of(p);
+        const bool forced = p.fx != 0.0f || p.fy != 0.0f;
+        const V2 Fx = splat<V2>(p.fx), Fy = splat<V2>(p.fy);
+        V2 acc0 = splat<V2>(0.f), acc1 = acc0, acc2 = acc0;
 #pragma unroll
         for (int hf = 0; hf < 2; hf++) {
             const Mom<V2> m = moments_v(g[hf]);
@@ -543,61 +526,50 @@ __global__ void __launch_bounds__(BX, LBM_TMA_MIN_BLOCKS) step_tma_kernel(const 
             else if (COLL == C_CM) collide_cm_v<false>(rx, g[hf], ux, uy, forced, Fx, Fy, splat<V2>(1.0f));
             else {
                 const V2 jm = jmag_v(ux, uy, m.rho), pm = pi_norm_v(m);
-                acc0 = acc0 + m.rho; acc1 = acc1 + jm; acc2 = acc2 + pm;
+                const bool z0 = (skip >> (2 * hf)) & 1u, z1 = (skip >> (2 * hf + 1)) & 1u;
+                acc0 = acc0 + zero_lanes(m.rho, z0, z1); acc1 = acc1 + zero_lanes(jm, z0, z1); acc2 = acc2 + zero_lanes(pm, z0, z1);
                 collide_cm_v<true>(rx, g[hf], ux, uy, forced, Fx, Fy, optimal_rate_v(m.rho, jm, pm, av));
             }
         }
+        if (COLL == C_CMOPT) { s0 = hsum(acc0); s1 = hsum(acc1); s2 = hsum(acc2); }
+        const bool k0 = !(skip & 1u), k1 = !(skip & 2u), k2 = !(skip & 4u), k3 = !(skip & 8u);
         if (p.rho_out) {
-            const long long ln = (long long)yl * p.nx + x0;
-            st4(p.rho_out + ln, rho4[0].x, rho4[0].y, rho4[1].x, rho4[1].y);
-            float* uo = reinterpret_cast<float*>(p.u_out + ln);
-            st4(uo, ux4[0].x, uy4[0].x, ux4[0].y, uy4[0].y);
-            st4(uo + 4, ux4[1].x, uy4[1].x, ux4[1].y, uy4[1].y);
+            const long long ln = (long long)yl * p.nx + x;
+            if (k0) { p.rho_out[ln] = rho4[0].x; p.u_out[ln] = make_float2(ux4[0].x, uy4[0].x); }
+            if (k1) { p.rho_out[ln + 32] = rho4[0].y; p.u_out[ln + 32] = make_float2(ux4[0].y, uy4[0].y); }
+            if (k2) { p.rho_out[ln + 64] = rho4[1].x; p.u_out[ln + 64] = make_float2(ux4[1].x, uy4[1].x); }
+            if (k3) { p.rho_out[ln + 96] = rho4[1].y; p.u_out[ln + 96] = make_float2(ux4[1].y, uy4[1].y); }
         }
-        // results back into the stage, in place (a lane reads and writes only its own 16 bytes of every box)
+        {
+            float* r = p.A0[gen] + r0 + x;
+            if (k0) r[0] = g[0][0].a.x;
+            if (k1) r[32] = g[0][0].a.y;
+            if (k2) r[64] = g[1][0].a.x;
+            if (k3) r[96] = g[1][0].a.y;
+        }
 #pragma unroll
-        for (int q = 0; q < Q; q++)
-            *reinterpret_cast<float4*>(buf + q * SEG) = make_float4(g[0][q].a.x, g[0][q].a.y, g[1][q].a.x, g[1][q].a.y);
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) {
-            const int xs = (sg % nsx) * SEG;
-            const float* src = wbuf + st * TMA_STAGE_FLOATS;
-            tma_store_box(&tmap, src, xs, yl + 1, a.rest_plane[gen]);
-#pragma unroll
-            for (int q = 1; q < Q; q++)                         // f*_q(x) -> A[q][x + c_q]
-                tma_store_box(&tmap, src + q * SEG, xs + cx(q), (cy(q) > 0 ? yp : (cy(q) < 0 ? ym : yl)) + 1, q);
-            tma_commit();
+        for (int q = 1; q < Q; q++) {
+            // f*_q(x) -> A[q][x + c_q]: destination row y + c_y, destination column x + c_x
+            float* r = cy(q) > 0 ? bp + q * sp : (cy(q) < 0 ? bm + q * sm : p.A[q] + r0);
+            const int d0 = cx(q) > 0 ? x + 1 : (cx(q) < 0 ? xw_lo : x);
+            const int d3 = cx(q) > 0 ? xw_hi : (cx(q) < 0 ? x + 95 : x + 96);
+            if (k0) r[d0] = g[0][q].a.x;
+            if (k1) r[x + 32 + cx(q)] = g[0][q].a.y;
+            if (k2) r[x + 64 + cx(q)] = g[1][q].a.x;
+            if (k3) r[d3] = g[1][q].a.y;
         }
-        // the clipped ends: f*_q of cell nx-1 with c_x = +1 goes to x = 0, of cell 0 with c_x = -1 to x = nx-1
-        if (last) {
-            p.A[1][rowoff(p, yl)] = g[1][1].a.y; p.A[5][rowoff(p, yp)] = g[1][5].a.y; p.A[8][rowoff(p, ym)] = g[1][8].a.y;
-        }
-        if (first) {
-            p.A[3][rowoff(p, yl) + p.nx - 1] = g[0][3].a.x; p.A[6][rowoff(p, yp) + p.nx - 1] = g[0][6].a.x; p.A[7][rowoff(p, ym) + p.nx - 1] = g[0][7].a.x;
-        }
-        sg = nxt;
-        st = (st + 1) % TMA_STAGES;
     }
-    if (lane == 0) tma_wait_all();                              // the bulk stores must have landed before the block gives up its shared memory
-    if (COLL == C_CMOPT && a.partials) block_partials(hsum(acc0), hsum(acc1), hsum(acc2), a.partials + 3 * (long long)blockIdx.x);
+    if (COLL == C_CMOPT && p.partials) block_partials(s0, s1, s2, p.partials + 3 * ((long long)blockIdx.y * gridDim.x + blockIdx.x));
 }
 
 // moments pre-pass for LBM_ADAPTER_EXACT: the grid sums of the CURRENT post-stream state, before any cell collides.
 // Same two launch shapes as the step: this scalar kernel over the whole slab or over the listed general segments ...
 template <bool ODD>
 __global__ void __launch_bounds__(BX) moments_kernel(const Params p) {
-    int x, yl;
-    if (p.gen_list) {
-        const int seg = p.gen_list[blockIdx.x];
-        yl = seg / p.nsx;
-        x = (seg - yl * p.nsx) * SEG + threadIdx.x;
-    } else {
-        x = blockIdx.x * BX + threadIdx.x;
-        yl = blockIdx.y;
-    }
+    int x = 0, yl = 0;
+    const bool on = general_cell_of_thread(p, x, yl);
     float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-    if (x < p.nx) {
+    if (on) {
         NodeState s;
         node_pre_collision<ODD, true>(p, x, yl, s);
         const V1 rho{s.m.rho};
@@ -621,7 +593,8 @@ __global__ void __launch_bounds__(BX, 6) moments_vec_kernel(const Params p) {
             const Mom<V2> m = moments_v(g[hf]);
             V2 ux = m.ux, uy = m.uy;
             if (forced) { const V2 hr = m.inv_rho * 0.5f; ux = fma(splat<V2>(p.fx), hr, ux); uy = fma(splat<V2>(p.fy), hr, uy); }
-            acc0 = acc0 + m.rho; acc1 = acc1 + jmag_v(ux, uy, m.rho); acc2 = acc2 + pi_norm_v(m);
+            const bool z0 = (c.skip >> (2 * hf)) & 1u, z1 = (c.skip >> (2 * hf + 1)) & 1u;
+            acc0 = acc0 + zero_lanes(m.rho, z0, z1); acc1 = acc1 + zero_lanes(jmag_v(ux, uy, m.rho), z0, z1); acc2 = acc2 + zero_lanes(pi_norm_v(m), z0, z1);
         }
         if (c.act) { s0 = hsum(acc0); s1 = hsum(acc1); s2 = hsum(acc2); }
     }
@@ -737,21 +710,26 @@ __global__ void signal_neighbours_kernel(unsigned long long* lo_flag, unsigned l
     __threadfence_system();
 }
 
-// one thread per segment: does any of its cells need the general path?
-__global__ void build_segmask_kernel(const Params p, uint8_t* mask) {
+// one thread per segment: SEG_VEC / SEG_GENERAL / SEG_MIXED (allow_mixed = 0: a segment with any general cell is SEG_GENERAL as a
+// whole — grids whose rows are not whole segments keep the shuffle-based odd kernel, which has no per-cell skipping)
+__global__ void build_segmask_kernel(const Params p, uint8_t* mask, int allow_mixed) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)p.nsx * p.nyl) return;
-    const int yl = (int)(i / p.nsx), sx = (int)(i - (long long)yl * p.nsx), yg = p.y0 + yl;
-    bool gen = p.force_plane != nullptr;
-    if (!p.py && (yg == 0 || yg == p.ny - 1)) gen = true;
-    if (!p.px && (sx == 0 || sx == p.nsx - 1)) gen = true;
-    if (!gen && p.flags) {
-        const int x1 = min(p.nx, (sx + 1) * SEG);
-        const uint8_t* f = p.flags + (long long)yl * p.nx;
-        for (int x = sx * SEG; x < x1; x++) if (f[x]) { gen = true; break; }
-    }
-    mask[i] = gen ? 1 : 0;
+    const int yl = (int)(i / p.nsx), sx = (int)(i - (long long)yl * p.nsx);
+    if (p.force_plane) { mask[i] = SEG_GENERAL; return; }
+    const int x1 = min(p.nx, (sx + 1) * SEG);
+    int n = 0;
+    for (int x = sx * SEG; x < x1; x++) n += cell_is_general(p, x, yl) ? 1 : 0;
+    mask[i] = n == 0 ? SEG_VEC : ((n == x1 - sx * SEG || !allow_mixed) ? SEG_GENERAL : SEG_MIXED);
 }
+// the general cells of the SEG_MIXED segments, as local node ids (thrust::copy_if predicate)
+struct mixed_general_cell {
+    Params p; const uint8_t* mask;
+    __device__ bool operator()(long long ln) const {
+        const int yl = (int)(ln / p.nx), x = (int)(ln - (long long)yl * p.nx);
+        return mask[(long long)yl * p.nsx + x / SEG] == SEG_MIXED && cell_is_general(p, x, yl);
+    }
+};
 
 // ------------------------------------------------------------------ IBM
 struct IbmData {

@@ -427,42 +427,45 @@ def test_run_from_host_on_peer_mapped_slabs(nx, ny, world, coll, nsteps):
     assert np.array_equal(fs, f1)
 
 
-# ---------------------------------------------------------------- odd phase through TMA (nx a multiple of 128)
-def _steps_fields(case, nsteps, quirks=63, adapter_mode=0, tma=True):
+# ---------------------------------------------------------------- rows of whole 128-cell segments: lane-interleaved odd kernel, mixed segments
+def _steps_fields(case, nsteps, quirks=63, adapter_mode=0, odd_kernel=True):
     import os
-    old = os.environ.get("LBM_B200_TMA")
-    os.environ["LBM_B200_TMA"] = "1" if tma else "0"       # read by lbm_create
+    old = os.environ.get("LBM_B200_ODD")
+    os.environ["LBM_B200_ODD"] = "1" if odd_kernel else "0"       # read by lbm_create
     try:
         e = make_engine(case, quirks, adapter_mode)
     finally:
         if old is None:
-            del os.environ["LBM_B200_TMA"]
+            del os.environ["LBM_B200_ODD"]
         else:
-            os.environ["LBM_B200_TMA"] = old
+            os.environ["LBM_B200_ODD"] = old
     e.init_fields(*case.init_fields())
     e.step(nsteps, macroscopics=True)
-    out = e.macroscopics(), e.populations()
+    out = e.macroscopics(), e.populations(), e.info()
     e.close()
     return out
 
 
-TMA_CASES = [("tg", 256, 48, (True, True), cases.BGK), ("tg", 384, 40, (True, True), cases.MRT), ("tg", 128, 36, (True, True), cases.CM),
+SEG_CASES = [("tg", 256, 48, (True, True), cases.BGK), ("tg", 384, 40, (True, True), cases.MRT), ("tg", 128, 36, (True, True), cases.CM),
              ("tg", 512, 24, (True, True), cases.CM_OPT), ("pois", 256, 24, (True, False), cases.MRT), ("lid", 384, 40, (False, False), cases.CM_OPT),
-             ("cyl_ibm", 384, 64, (False, False), cases.MRT), ("cyl_flag", 256, 64, (False, False), cases.BGK)]
+             ("lid", 256, 33, (False, False), cases.BGK), ("cyl_ibm", 384, 64, (False, False), cases.MRT), ("cyl_flag", 256, 64, (False, False), cases.BGK),
+             ("cyl_ibm", 512, 48, (False, False), cases.CM_OPT)]
 
 
-@pytest.mark.parametrize("kind,nx,ny,periodic,coll", TMA_CASES)
-def test_tma_odd_phase_equals_the_shuffle_kernel_and_the_oracle(kind, nx, ny, periodic, coll):
-    """Grids whose rows are whole 128-cell segments take the odd AA phase through step_tma_kernel (tensor-map tile copies with the
-    one-cell x shift in the box coordinates).  Same per-cell arithmetic as the shuffle-based kernel: bit-identical fields; and the
-    usual fp32 bounds against the CPU oracle."""
+@pytest.mark.parametrize("kind,nx,ny,periodic,coll", SEG_CASES)
+def test_interleaved_odd_kernel_and_mixed_segments(kind, nx, ny, periodic, coll):
+    """Grids whose rows are whole 128-cell segments: the odd AA phase runs in step_odd_kernel (lane l of a warp owns cells l, l + 32,
+    l + 64, l + 96 of the segment: 32-bit coalesced accesses, no shuffles), and segments that hold a few general cells (wall ends of a
+    row, nodes under marker stencils, CYLINDER flags) are MIXED: the vectorised kernels skip exactly those cells and the general kernel
+    takes them from a per-cell list.  With LBM_B200_ODD=0 the shuffle-based odd kernel and whole-segment general lists are used instead.
+    Every cell gets the same arithmetic either way: bit-identical fields; and the usual fp32 bounds against the CPU oracle."""
     nu = 1.0 / 6.0 if kind in ("tg", "pois") else (0.03 if kind == "lid" else float(cases._cyl_nu(ny)))
     um = {"tg": 0.04, "pois": 0.05, "lid": 0.1}.get(kind, 0.05)
     force = cases._pois_force(ny) if kind == "pois" else (0.0, 0.0)
-    case = cases.Case(f"tma_{kind}_{nx}x{ny}", nx, ny, coll, nu, periodic, um, kind, force=force, np_markers=24, scale=nx // 128)
+    case = cases.Case(f"seg_{kind}_{nx}x{ny}", nx, ny, coll, nu, periodic, um, kind, force=force, np_markers=24, scale=nx // 128)
     n = 9
-    (rho_t, u_t), f_t = _steps_fields(case, n, tma=True)
-    (rho_s, u_s), f_s = _steps_fields(case, n, tma=False)
+    (rho_t, u_t), f_t, info_t = _steps_fields(case, n, odd_kernel=True)
+    (rho_s, u_s), f_s, info_s = _steps_fields(case, n, odd_kernel=False)
     assert np.isfinite(f_t).all()
     assert np.array_equal(f_t, f_s) and np.array_equal(rho_t, rho_s) and np.array_equal(u_t, u_s), float(np.abs(f_t - f_s).max())
     o = make_oracle(case)
@@ -473,20 +476,29 @@ def test_tma_odd_phase_equals_the_shuffle_kernel_and_the_oracle(kind, nx, ny, pe
 
 
 @pytest.mark.parametrize("coll,world,chunk,direct", [(cases.BGK, 2, 7, True), (cases.MRT, 3, 4, True), (cases.CM_OPT, 3, 7, "all"), (cases.CM, 2, 1, False)])
-def test_tma_odd_phase_on_slabs(coll, world, chunk, direct):
-    """Slabs: interior rows take the TMA kernel, the two rows that pull from a peer-mapped neighbour the shuffle kernel (one-row bands)."""
-    case = cases.Case("tma_slabs", 256, 36, coll, 1.0 / 6.0, (True, True), 0.04, "tg", scale=2)
+def test_interleaved_odd_kernel_on_slabs(coll, world, chunk, direct):
+    """Slabs: the odd kernel reaches rows y - 1 / y + 1 of a peer-mapped neighbour through the same row pointers as the shuffle kernel."""
+    case = cases.Case("seg_slabs", 256, 36, coll, 1.0 / 6.0, (True, True), 0.04, "tg", scale=2)
     nsteps = 7
     rho_s, u_s, f_s = _run_slabs(case, world, nsteps, direct=direct, chunk=chunk)
-    (rho_1, u_1), f_1 = _steps_fields(case, nsteps)
+    (rho_1, u_1), f_1, _ = _steps_fields(case, nsteps)
     tol = 0.0 if coll != cases.CM_OPT else 2e-7
     assert np.abs(f_s - f_1).max() <= tol and np.abs(rho_s - rho_1).max() <= tol and np.abs(u_s - u_1).max() <= tol
 
 
-def test_tma_lagged_adapter_partials():
-    """LBM_ADAPTER_LAGGED: the TMA kernel forms one partial triple per persistent block, the shuffle kernel one per 512 cells — the
-    grid means agree to fp32 summation order."""
-    case = cases.Case("tma_lag", 512, 64, cases.CM_OPT, 0.03, (False, False), 0.1, "lid")
-    (rho_t, u_t), f_t = _steps_fields(case, 12, adapter_mode=1, tma=True)
-    (rho_s, u_s), f_s = _steps_fields(case, 12, adapter_mode=1, tma=False)
+@pytest.mark.parametrize("world,direct", [(2, "all"), (3, False)])
+def test_mixed_segments_on_slabs_with_a_body(world, direct):
+    case = cases.Case("seg_slabs_ibm", 256, 48, cases.MRT, cases._cyl_nu(48), (False, False), 0.05, "cyl_ibm", np_markers=24)
+    nsteps = 7
+    rho_s, u_s, f_s = _run_slabs(case, world, nsteps, direct=direct, chunk=3)
+    (rho_1, u_1), f_1, _ = _steps_fields(case, nsteps)
+    assert np.array_equal(f_s, f_1) and np.array_equal(rho_s, rho_1) and np.array_equal(u_s, u_1)
+
+
+def test_lagged_adapter_with_mixed_segments():
+    """LBM_ADAPTER_LAGGED: block partials are grouped differently by the two odd kernels and the two general launch shapes — the grid
+    means agree to fp32 summation order."""
+    case = cases.Case("seg_lag", 512, 64, cases.CM_OPT, 0.03, (False, False), 0.1, "lid")
+    (rho_t, u_t), f_t, _ = _steps_fields(case, 12, adapter_mode=1, odd_kernel=True)
+    (rho_s, u_s), f_s, _ = _steps_fields(case, 12, adapter_mode=1, odd_kernel=False)
     assert np.isfinite(f_t).all() and np.abs(f_t - f_s).max() <= 1e-6, float(np.abs(f_t - f_s).max())
