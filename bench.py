@@ -159,19 +159,23 @@ def reference_cuda_mlups(binary, steps, timeout=600):
             "what": "the reference's own translation units (src/core, src/IBM) compiled for sm_100a by oracle/build_ref.sh; median-free mean of its per-step CUDA-event times"}
 
 
-# name -> (shim binary, reference binary, nx, ny, operator, warm-up steps, timed steps, reference steps, description)
+# name -> (shim binary, reference binary, nx, ny, operator, warm-up steps, timed steps, reference steps, description); c3 repeats its
+# (init, warm-up, timed) segment C3_REPEAT times
 CONFIGS = {
     "c1": ("ex_c1_tg_256", "c1_tg_bgk_256", 256, 256, "BGK", 64, 4000, 200, "Taylor-Green 256x256 BGK (configs[0])"),
     "c2": ("ex_c2_pois_1024x256", "c2_pois_mrt_1024x256", 1024, 256, "MRT", 64, 4000, 200, "Poiseuille 1024x256 MRT, body force, bounce-back walls (configs[1])"),
     # 18 + 17 steps: the reference's adapter keeps this cavity physical for ~40 steps (tools/c3_probe.py, profiles/r02_c3_probe.txt); the
     # warm-up covers module load and the capture of the 16-step CUDA graph that the timed steps replay (same parity)
-    "c3": ("ex_c3_lid_4096", "c3_lid_cmopt_4096", 4096, 4096, "CM<OptimalAdapter> (exact grid means)", 18, 17, 36,
+    "c3": ("ex_c3_lid_4096", "c3_lid_cmopt_4096", 4096, 4096, "CM<OptimalAdapter> (exact grid means)", 18, 17, 30,
            "lid-driven cavity 4096x4096 CM<OptimalAdapter> (configs[2]); run inside the window in which the reference's adapter keeps the field finite"),
     "c3_lagged": ("ex_c3_lid_4096", None, 4096, 4096, "CM<OptimalAdapter> (grid means of the previous step)", 18, 17, 0,
                   "configs[2] with LBM_ADAPTER_LAGGED (72 B/cell; deviation from the exact mode: tests/test_reference_fullsize_gpu.py)"),
     "c5": ("ex_c5_cyl_8192x2048", "c5_cyl_ibm_mrt_8192x2048", 8192, 2048, "MRT + IBM (256 markers)", 32, 400, 60,
            "flow past cylinder 8192x2048 MRT, IBM direct forcing (configs[4])"),
 }
+
+
+C3_REPEAT = 6
 
 
 def run_config(name, peak):
@@ -184,7 +188,8 @@ def run_config(name, peak):
         env["LBM_B200_ADAPTER"] = "1"
     with tempfile.TemporaryDirectory() as tmp:
         try:
-            r = subprocess.run([path, "--steps", str(steps), "--save-int", str(steps), "--warmup", str(warm), "--fast"], cwd=tmp, env=env,
+            rep = C3_REPEAT if name.startswith("c3") else 1
+            r = subprocess.run([path, "--steps", str(steps), "--save-int", str(steps), "--warmup", str(warm), "--repeat", str(rep), "--fast"], cwd=tmp, env=env,
                                capture_output=True, text=True, timeout=600)
         except Exception as ex:  # noqa: BLE001
             return {"name": name, "error": str(ex)[:200]}
@@ -194,7 +199,7 @@ def run_config(name, peak):
     res = dict(kv.split("=") for kv in m.group(1).split())
     mlups, mass = float(res["mlups"]), float(res["mass_per_node"])
     cells = nx * ny
-    out = {"name": name, "workload": what, "nx": nx, "ny": ny, "collision": op, "warmup_steps": warm, "steps": steps,
+    out = {"name": name, "workload": what, "nx": nx, "ny": ny, "collision": op, "warmup_steps": warm, "steps": steps, "segments": rep,
            "mlups": mlups, "ms_per_step": float(res["ms_per_step"]),
            "physical": bool(abs(mass - 1.0) < 0.05 and float(res["sum_u2"]) == float(res["sum_u2"])), "mass_per_node": mass,
            "api": "examples/main.cu over the LBM<2> / ScenarioTrait header shim (include/cuda-lbm), LBM::run<Scenario>(n)"}

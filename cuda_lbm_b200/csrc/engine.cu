@@ -311,6 +311,12 @@ static int ensure_flags(lbm_handle* h) {
 }
 
 static int rebuild_ibm(lbm_handle* h);
+// Everything a step builds lazily (segment classification and lists via thrust, partial-sum buffers: cudaMalloc and stream
+// synchronisation inside) is settled by the calls that change the configuration and by the init calls, never inside lbm_step: with
+// peer-mapped slabs stepping from several host threads, a cudaMalloc (a device-wide synchronisation) issued by one slab's first step
+// while another slab's handshake kernel already spins for it would dead-lock until the handshake timeout.
+static int prepare_resources(lbm_handle* h, bool want_macros);
+static int settle(lbm_handle* h) { return h->direct() ? prepare_resources(h, false) : LBM_OK; }
 
 extern "C" int lbm_set_flags(lbm_handle* h, const int32_t* flags) {
     if (!h || !flags) return fail(LBM_ERR_INVALID, "NULL argument");
@@ -367,7 +373,7 @@ extern "C" int lbm_set_flags(lbm_handle* h, const int32_t* flags) {
     }
     h->segs_dirty = true;
     if (!h->h_pts.empty()) return rebuild_ibm(h);       // re-mark the IBM bit
-    return LBM_OK;
+    return settle(h);
 }
 
 extern "C" int lbm_set_body_force(lbm_handle* h, float fx, float fy) {
@@ -383,12 +389,12 @@ extern "C" int lbm_set_force_field(lbm_handle* h, const float* force_aos) {
     CU(cudaStreamSynchronize(h->stream));
     if (!force_aos) {
         if (h->force_plane) { cudaFree(h->force_plane); h->bytes -= (long long)h->nloc * (long long)sizeof(float2); h->force_plane = nullptr; h->segs_dirty = true; }
-        return LBM_OK;
+        return settle(h);
     }
     if (!h->force_plane) { CU(dmalloc(h, &h->force_plane, (size_t)h->nloc)); h->segs_dirty = true; }
     CU(cudaMemcpyAsync(h->force_plane, force_aos + (size_t)2 * h->y0 * h->cfg.nx, (size_t)h->nloc * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));
-    return LBM_OK;
+    return settle(h);
 }
 
 extern "C" int lbm_set_force_field_device(lbm_handle* h, const float* d_force) {
@@ -398,7 +404,7 @@ extern "C" int lbm_set_force_field_device(lbm_handle* h, const float* d_force) {
     // stream-ordered behind the steps already enqueued; the caller's buffer may be reused once the call returns
     CU(cudaMemcpyAsync(h->force_plane, d_force, (size_t)h->nloc * sizeof(float2), cudaMemcpyDeviceToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));
-    return LBM_OK;
+    return settle(h);
 }
 
 

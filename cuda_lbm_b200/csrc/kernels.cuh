@@ -457,7 +457,7 @@ __global__ void __launch_bounds__(BX, vec_min_blocks(COLL, ODD)) step_vec_kernel
 // packed pair are loaded straight into a register pair, and there is nothing to shuffle, predicate or re-pair.  Same per-cell
 // arithmetic as every other kernel (bit-identical results).  Needs rows made of whole segments (nx % 128 == 0).
 #ifndef LBM_ODD_MIN_BLOCKS
-#define LBM_ODD_MIN_BLOCKS 5
+#define LBM_ODD_MIN_BLOCKS 4      // 5 (<= 102 registers) spills 16 bytes and loses 1.3 % (profiles/r02_kbench_odd_kernel.txt)
 #endif
 #ifndef LBM_ODD_MIN_BLOCKS_OPT
 #define LBM_ODD_MIN_BLOCKS_OPT 4

@@ -10,6 +10,8 @@
 //
 //   ./tg [--steps N] [--save-int K] [--warmup W] [--vtk] [--dump] [--fast] [--load-ckpt FILE] [--save-ckpt FILE]
 //     --warmup W    W untimed steps first (module load, CUDA-graph capture); --steps counts the timed steps that follow
+//     --repeat R    the whole segment (init, warm-up, timed steps) R times; times add up (for scenarios that stay physical for a
+//                   limited number of steps only, e.g. CM<2,OptimalAdapter> on the impulsively started cavity)
 //     --save-int K  every K steps: update_macroscopics + compute_error (and --vtk: save_vtk, --dump: save_macroscopics)
 //     --fast        no per-step host calls between save points (LBM::run), the throughput mode
 //     --load-ckpt F continue from a checkpoint written by --save-ckpt (same binary); --steps counts the steps still to run
@@ -43,13 +45,14 @@ using Scenario = FlowPastCylinderScenario;
 #endif
 
 int main(int argc, char** argv) {
-    int total_timesteps = 1000, save_int = 100, warmup = 0;
+    int total_timesteps = 1000, save_int = 100, warmup = 0, repeat = 1;
     bool vtk = false, dump = false, fast = false;
     const char *load_ckpt = nullptr, *save_ckpt = nullptr;
     for (int i = 1; i < argc; i++) {
         if (!strcmp(argv[i], "--steps") && i + 1 < argc) total_timesteps = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--save-int") && i + 1 < argc) save_int = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--warmup") && i + 1 < argc) warmup = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "--repeat") && i + 1 < argc) repeat = std::max(1, atoi(argv[++i]));
         else if (!strcmp(argv[i], "--vtk")) vtk = true;
         else if (!strcmp(argv[i], "--dump")) dump = true;
         else if (!strcmp(argv[i], "--fast")) fast = true;
@@ -73,16 +76,17 @@ int main(int argc, char** argv) {
         lbm.load_checkpoint<Scenario>(load_ckpt);
         printf("restarted from %s at step %d\n", load_ckpt, lbm.timestep);
     }
+    cudaEvent_t start, stop;
+    cudaEventCreate(&start);
+    cudaEventCreate(&stop);
+    float last_error = -1.0f, gpu_ms = 0.0f;
+    for (int rep = 0; rep < repeat; rep++) {
+    if (rep > 0) lbm.init<Scenario>();
     if (warmup > 0) {
         lbm.run<Scenario>(warmup);
         lbm.synchronize();
     }
     const int first_step = lbm.timestep;
-
-    cudaEvent_t start, stop;
-    cudaEventCreate(&start);
-    cudaEventCreate(&stop);
-    float last_error = -1.0f, gpu_ms = 0.0f;
     int t = 0;
     while (t < total_timesteps) {
         const int chunk = std::min(save_int, total_timesteps - t);
@@ -128,6 +132,7 @@ int main(int argc, char** argv) {
 #endif
         }
     }
+    }
     if (save_ckpt) {
         lbm.save_checkpoint(save_ckpt);
         printf("checkpoint of step %d written to %s\n", lbm.timestep, save_ckpt);
@@ -137,8 +142,8 @@ int main(int argc, char** argv) {
     for (size_t i = 0; i < lbm.h_rho.size(); i++) sum_rho += lbm.h_rho[i];
     for (size_t i = 0; i < lbm.h_u.size(); i++) sum_u2 += (double)lbm.h_u[i] * lbm.h_u[i];
     printf("SHIM_RESULT scenario=%s gpus=%d nx=%d ny=%d steps=%d ms_per_step=%.6f mlups=%.3f error_pct=%.6f mass_per_node=%.9f mean_rho=%.9f sum_u2=%.9e\n",
-           Scenario::name(), lbm.num_slabs(), NX, NY, total_timesteps, gpu_ms / total_timesteps,
-           lbm_b200_mlups((long long)NX * NY, total_timesteps, gpu_ms * 1e-3), last_error, mass / ((double)NX * NY),
+           Scenario::name(), lbm.num_slabs(), NX, NY, total_timesteps * repeat, gpu_ms / (total_timesteps * repeat),
+           lbm_b200_mlups((long long)NX * NY, (long long)total_timesteps * repeat, gpu_ms * 1e-3), last_error, mass / ((double)NX * NY),
            sum_rho / ((double)NX * NY), sum_u2);
     return 0;
 }

@@ -35,6 +35,7 @@ def main():
     ap.add_argument("--mode", default="direct")
     ap.add_argument("--coll", type=int, default=cases.MRT)
     ap.add_argument("--steps", type=int, default=21)
+    ap.add_argument("--adapter", type=int, default=0, help="0 = LBM_ADAPTER_EXACT, 1 = LBM_ADAPTER_LAGGED (OptimalAdapter only)")
     ap.add_argument("--from-host", action="store_true", help="one lbm_run_from_host call per rank instead of init + steps + read-back")
     a = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
@@ -43,11 +44,11 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     case = build_case(a.kind, a.coll)
     rho0, u0 = case.init_fields()
-    e = cases.make_engine(case, device=local, rank=rank, world=world)
+    e = cases.make_engine(case, adapter_mode=a.adapter, device=local, rank=rank, world=world)
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     e.set_stream(stream.cuda_stream)
-    s = SlabSolver(e, case.nx, case.periodic[1], dev, optimal_adapter=(case.coll == cases.CM_OPT), adapter_exact=True, mode=a.mode)
+    s = SlabSolver(e, case.nx, case.periodic[1], dev, optimal_adapter=(case.coll == cases.CM_OPT), adapter_exact=(a.adapter == 0), mode=a.mode)
     if a.from_host:
         # pinned host slabs in, pinned host slabs out: the band pipeline of every rank, slab faces synchronised on the device
         sl = slice(e.y0, e.y0 + e.ny_local)
@@ -69,7 +70,7 @@ def main():
     ok = True
     if rank == 0:
         full = torch.cat(parts, dim=0).cpu().numpy()
-        one = cases.make_engine(case, device=local)
+        one = cases.make_engine(case, adapter_mode=a.adapter, device=local)
         one.init_fields(rho0, u0)
         one.step(a.steps, macroscopics=True)
         r1, u1 = one.macroscopics()

@@ -26,7 +26,8 @@ def _port():
 
 @pytest.mark.parametrize("kind,mode,coll,extra", [("tg", "direct", 0, ()), ("tg", "nccl", 1, ()), ("ibm", "direct", 1, ()), ("ibm", "nccl", 1, ()),
                                                   ("ibm", "direct", 3, ()), ("ibm", "nccl", 3, ()), ("tg", "direct", 1, ("--from-host",)),
-                                                  ("tg", "nccl", 0, ("--from-host",))])
+                                                  ("tg", "nccl", 0, ("--from-host",)),
+                                                  ("tg", "nccl", 3, ("--adapter", "1")), ("tg", "direct", 3, ("--adapter", "1")), ("ibm", "direct", 3, ("--adapter", "1"))])
 def test_slabs_across_processes_match_single_gpu(kind, mode, coll, extra):
     n = min(_ngpu(), 4)
     if n < 2:

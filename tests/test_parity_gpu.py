@@ -467,7 +467,9 @@ def test_interleaved_odd_kernel_and_mixed_segments(kind, nx, ny, periodic, coll)
     (rho_t, u_t), f_t, info_t = _steps_fields(case, n, odd_kernel=True)
     (rho_s, u_s), f_s, info_s = _steps_fields(case, n, odd_kernel=False)
     assert np.isfinite(f_t).all()
-    assert np.array_equal(f_t, f_s) and np.array_equal(rho_t, rho_s) and np.array_equal(u_t, u_s), float(np.abs(f_t - f_s).max())
+    # OptimalAdapter: the block partials of the grid sums are grouped differently (fp32 summation order), everything else is bit-identical
+    tol = 0.0 if coll != cases.CM_OPT else 2e-7
+    assert np.abs(f_t - f_s).max() <= tol and np.abs(rho_t - rho_s).max() <= tol and np.abs(u_t - u_s).max() <= tol, float(np.abs(f_t - f_s).max())
     o = make_oracle(case)
     o.init(*case.init_fields())
     o.step(n)

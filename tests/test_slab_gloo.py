@@ -55,7 +55,11 @@ class FakeEngine:
         self.set_sums.append(list(s))
 
     def adapter_prepass(self):
-        pass
+        self.calls.append(("prepass", self.t))
+
+    def adapter_sums_pending(self):
+        """lagged mode: only the first step after init has no sums from a previous step"""
+        return self.t == 0
 
     # driver segment from / to host memory (SlabSolver.run_from_host, halo coupling = the three calls with a barrier)
     def init_fields_local(self, rho_ptr, u_ptr):
@@ -87,8 +91,14 @@ class FakeEngine:
 def _worker(rank, world, port, periodic, optimal, q, ibm_floats=0):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    e = FakeEngine(rank, world, ibm_floats)
-    s = SlabSolver(e, NX, periodic, torch.device("cpu"), optimal_adapter=optimal, adapter_exact=True)
+    e = FakeEngine(rank, world, ibm_floats if ibm_floats != -2 else 0)
+    s = SlabSolver(e, NX, periodic, torch.device("cpu"), optimal_adapter=optimal, adapter_exact=(ibm_floats != -2))
+    if ibm_floats == -2:            # OptimalAdapter with the grid means of the previous step (LBM_ADAPTER_LAGGED)
+        s.step(4)
+        q.put((rank, e.calls, e.set_sums, s.collectives))
+        dist.barrier()
+        dist.destroy_process_group()
+        return
     if ibm_floats == -1:            # the driver-segment call instead of plain stepping
         e.ibm_floats = 0
         s.run_from_host(11, 12, 4, 13, 14)
@@ -152,6 +162,15 @@ def test_optimal_adapter_allreduce_every_step():
     for rank, (_, sums, ncoll) in res.items():
         assert ncoll == 4 and len(sums) == 4
         assert sums[0] == [3.0, 4.0, 6.0]        # (1+0)+(1+1), 2+2, 3+3
+
+
+def test_lagged_optimal_adapter_bootstraps_the_first_step():
+    """LBM_ADAPTER_LAGGED on several slabs with the halo coupling: the sums come out of each step (one all-reduce after it), except before
+    the very first step, which has no predecessor: a moments pre-pass + all-reduce bootstraps it (5 collectives for 4 steps)."""
+    res = _run(2, True, optimal=True, ibm_floats=-2)
+    for rank, (calls, sums, ncoll) in res.items():
+        assert [c for c in calls if c[0] == "prepass"] == [("prepass", 0)], calls
+        assert ncoll == 5 and len(sums) == 5
 
 
 @pytest.mark.parametrize("world", [2, 3])

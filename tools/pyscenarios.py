@@ -81,7 +81,7 @@ class ScenarioTrait:
         self.tau = viscosity_to_tau(self.viscosity)
         self.omega = f32(1.0) / self.tau
         if self.S is None:
-            from .solver import default_S
+            from cuda_lbm_b200.solver import default_S
             self.S = default_S(self.collision, self.omega)
         self.S = np.asarray(self.S, f32)
 
