@@ -65,14 +65,18 @@ template <class V>
 LBM_HD V jmag_v(V ux, V uy, V rho) { return vsqrt(fma(ux, ux, uy * uy)) * rho; }
 
 // ------------------------------------------------------------------ BGK with Guo forcing
-// Directions come in opposite pairs (q, opp q) with c.u of opposite sign:  f_eq(+-) = w rho (c1 + 4.5 cu^2) +- 3 w rho cu
-// with c1 = 1 - 1.5 u^2, and the Guo term (+-) = w k (9 cu cF - 3 u.F) +- 3 w k cF with k = 1 - omega/2.  The relaxation
+// Directions come in opposite pairs (q, opp q) with c.u of opposite sign:  f_eq(+-) = w rho (1 + e2) +- 3 w rho cu with the
+// second-order part e2 = 4.5 cu^2 - 1.5 u^2, and the Guo term (+-) = w k (9 cu cF - 3 u.F) +- 3 w k cF with k = 1 - omega/2.  The relaxation
 // f' = (1 - omega) f + omega f_eq + force is evaluated as one FMA per direction on the shared symmetric / antisymmetric parts.
+// e2 (~Ma^2) is kept apart from the 1 and enters through an FMA, omega w rho (1 + e2) = fma(orw, e2, orw): formed as 1 + e2 first, its
+// rounding (6e-8, the same for all nine directions of a cell) is a mass error per cell and step that acts as pressure noise — at
+// |u| ~ 6e-4 (8192^2 Taylor-Green) it tripled the analytic error relative to the reference, whose f_eq bracket is evaluated in double
+// (equilibrium.cu:7-37, A-D19); with the FMA form the engine is as accurate (tests/test_reference_fullsize_gpu.py).
 template <class V>
-LBM_HD void bgk_pair(V& ga, V& gb, V cu, V cF, V c1, V m3uF, V orw, float onem, float k, float w, bool forced) {
+LBM_HD void bgk_pair(V& ga, V& gb, V cu, V cF, V m15usq, V m3uF, V orw, float onem, float k, float w, bool forced) {
     // ga: direction with +cu, gb: its opposite.  orw = omega * w * rho
-    const V sym0 = fma(cu * 4.5f, cu, c1);
-    V sym = orw * sym0;
+    const V e2 = fma(cu * 4.5f, cu, m15usq);
+    V sym = fma(orw, e2, orw);
     V anti = (orw * 3.0f) * cu;
     if (forced) {
         sym = fma(fma(cu * 9.0f, cF, m3uF), w * k, sym);
@@ -85,21 +89,22 @@ LBM_HD void bgk_pair(V& ga, V& gb, V cu, V cF, V c1, V m3uF, V orw, float onem, 
 template <class V>
 LBM_HD void collide_bgk_v(const Relax& r, V g[Q], V rho, V ux, V uy, bool forced, V Fx, V Fy) {
     const float om = r.omega, onem = 1.0f - om, k = 1.0f - 0.5f * om;
-    const V c1 = fma(fma(ux, ux, uy * uy), -1.5f, 1.0f);
+    const V m15usq = fma(ux, ux, uy * uy) * -1.5f;
     const V orho = rho * om;
     V m3uF = splat<V>(0.0f);
     if (forced) m3uF = fma(ux, Fx, uy * Fy) * -3.0f;
     // rest population: cu = cF = 0
     {
-        V s = (orho * (4.0f / 9.0f)) * c1;
+        const V orw0 = orho * (4.0f / 9.0f);
+        V s = fma(orw0, m15usq, orw0);
         if (forced) s = fma(m3uF, (4.0f / 9.0f) * k, s);
         g[0] = fma(g[0], onem, s);
     }
     const V orw1 = orho * (1.0f / 9.0f), orw2 = orho * (1.0f / 36.0f);
-    bgk_pair(g[1], g[3], ux, Fx, c1, m3uF, orw1, onem, k, 1.0f / 9.0f, forced);
-    bgk_pair(g[2], g[4], uy, Fy, c1, m3uF, orw1, onem, k, 1.0f / 9.0f, forced);
-    bgk_pair(g[5], g[7], ux + uy, Fx + Fy, c1, m3uF, orw2, onem, k, 1.0f / 36.0f, forced);
-    bgk_pair(g[6], g[8], uy - ux, Fy - Fx, c1, m3uF, orw2, onem, k, 1.0f / 36.0f, forced);
+    bgk_pair(g[1], g[3], ux, Fx, m15usq, m3uF, orw1, onem, k, 1.0f / 9.0f, forced);
+    bgk_pair(g[2], g[4], uy, Fy, m15usq, m3uF, orw1, onem, k, 1.0f / 9.0f, forced);
+    bgk_pair(g[5], g[7], ux + uy, Fx + Fy, m15usq, m3uF, orw2, onem, k, 1.0f / 36.0f, forced);
+    bgk_pair(g[6], g[8], uy - ux, Fy - Fx, m15usq, m3uF, orw2, onem, k, 1.0f / 36.0f, forced);
 }
 
 // ------------------------------------------------------------------ MRT
@@ -169,7 +174,7 @@ struct AdapterAvg { float inv_rho, inv_j, inv_pi; };
 LBM_HD float rate_of_tau_star(float t) {
     t = t > 0.0f ? t : 0.005f;          // also taken for NaN (0/0 grid mean of a fluid at rest), as in the reference
     t = fminf(t, 1.5f);
-    return 1.0f / fmaf(3.0f, t, 0.5f);
+    return fast_rcp(fmaf(3.0f, t, 0.5f));
 }
 LBM_HD V1 rate_of_tau_star(V1 t) { V1 r; r.a = rate_of_tau_star(t.a); return r; }
 LBM_HD V2 rate_of_tau_star(V2 t) { V2 r; r.a = make_float2(rate_of_tau_star(t.a.x), rate_of_tau_star(t.a.y)); return r; }

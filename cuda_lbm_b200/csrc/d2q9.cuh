@@ -348,7 +348,7 @@ __device__ __forceinline__ Relax relax_of(const Params& p) {
     return r;
 }
 __device__ __forceinline__ AdapterAvg load_adapter_avg(const float* avg) {
-    AdapterAvg a; a.inv_rho = 1.0f / avg[0]; a.inv_j = 1.0f / avg[1]; a.inv_pi = 1.0f / avg[2]; return a;
+    AdapterAvg a; a.inv_rho = fast_rcp(avg[0]); a.inv_j = fast_rcp(avg[1]); a.inv_pi = fast_rcp(avg[2]); return a;
 }
 
 }  // namespace lbm

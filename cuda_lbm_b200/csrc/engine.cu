@@ -55,6 +55,10 @@ struct lbm_handle {
     struct StepGraph { cudaGraphExec_t exec = nullptr; std::string key; long long launches = 0; int d_avg = 0, d_pre = 0, d_nbrg = 0; } graph[2];
     int graph_mode = -1;            // LBM_B200_GRAPH: 0 never, 1 whenever possible, unset = slabs of up to 2^22 cells
     cudaEvent_t ev_bridge[2] = {nullptr, nullptr};
+    // peer-mapped slabs: lbm_step(h, n) keeps at most 3 x 8 steps enqueued ahead of the device (events recorded every 8 steps, the
+    // host waits for the one of 24 steps ago).  Deeper queues gain nothing, and when several slabs share ONE device (tests, more slabs
+    // than GPUs) their blocked launches exhaust the context's launch queue while the slab they wait for cannot enqueue any more.
+    cudaEvent_t ev_throttle[3] = {nullptr, nullptr, nullptr};
     // lbm_run_from_host: copy streams and per-band events of the time-skewed pipeline (engine_pipeline.inc)
     cudaStream_t copy_in = nullptr, copy_out = nullptr; cudaEvent_t ev_pipe = nullptr; std::vector<cudaEvent_t> ev_band;
     unsigned long long pipe_epoch = 0;           // number of pipelined calls on several slabs (tags the level counters)      // legacy / per-thread user stream <-> own stream around graph replays
@@ -175,7 +179,7 @@ static void preload_kernels(int device) {
     done[device] = true;
     preload_coll<C_BGK>(); preload_coll<C_MRT>(); preload_coll<C_CM>(); preload_coll<C_CMOPT>();
     preload(moments_kernel<false>); preload(moments_kernel<true>); preload(moments_vec_kernel<false>); preload(moments_vec_kernel<true>);
-    preload(reduce_stage1_kernel); preload(reduce_stage2_kernel); preload(sums_to_avg_kernel); preload(adapter_collect_kernel);
+    preload(reduce_kernel); preload(sums_to_avg_kernel); preload(adapter_collect_kernel);
     preload(recover_macros_kernel<false>); preload(recover_macros_kernel<true>);
     preload(nbr_gather_kernel<false>); preload(nbr_gather_kernel<true>);
     preload(ibm_kernel<false>); preload(ibm_kernel<true>); preload(ibm_state_kernel<false>); preload(ibm_state_kernel<true>);
@@ -215,6 +219,7 @@ extern "C" int lbm_destroy(lbm_handle* h) {
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     for (auto& g : h->graph) if (g.exec) cudaGraphExecDestroy(g.exec);
     for (auto& e : h->ev_bridge) if (e) cudaEventDestroy(e);
+    for (auto& e : h->ev_throttle) if (e) cudaEventDestroy(e);
     for (auto& e : h->ev_band) cudaEventDestroy(e);
     if (h->ev_pipe) cudaEventDestroy(h->ev_pipe);
     if (h->copy_in) cudaStreamDestroy(h->copy_in);
@@ -279,7 +284,10 @@ extern "C" int lbm_create(const lbm_config* cfg, lbm_handle** out) {
               dmalloc(h, &h->ring, (size_t)2 * h->perim * Q) == cudaSuccess &&
               dmalloc(h, &h->sums, 3) == cudaSuccess && dmalloc(h, &h->avg, 3) == cudaSuccess &&
               dmalloc(h, &h->mass_acc, 1) == cudaSuccess;
-    if (ok && cfg->collision == LBM_CM_OPTIMAL) ok = dmalloc(h, &h->stage, (size_t)3 * RED_BLOCKS) == cudaSuccess;
+    if (ok && cfg->collision == LBM_CM_OPTIMAL) {     // fp64 triples of the reduction blocks + its ticket
+        ok = dmalloc(h, &h->stage, (size_t)3 * RED_BLOCKS + 1) == cudaSuccess;
+        if (ok) cudaMemsetAsync(h->stage, 0, ((size_t)3 * RED_BLOCKS + 1) * sizeof(double), h->stream);
+    }
     if (!ok) { std::string m = cudaGetErrorString(cudaGetLastError()); lbm_destroy(h); return fail(LBM_ERR_CUDA, "device allocation failed: " + m); }
     cudaMemsetAsync(h->pop, 0, (pop_floats + tail_floats) * sizeof(float), h->stream);
     cudaMemsetAsync(h->sync_timeout, 0, sizeof(int), h->stream);

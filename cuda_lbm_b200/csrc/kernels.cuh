@@ -92,6 +92,17 @@ __device__ __forceinline__ void block_partials(float a, float b, float c, float*
     }
 }
 
+// the vectorised kernels: one triple per WARP (slot = block * (BX / 32) + warp), no block-wide barrier — a warp retires as soon as its
+// own cells are done.  Warps that are switched off (general segment, beyond the row) write zeros.
+__device__ __forceinline__ void warp_partials(float a, float b, float c, float* block_out) {
+    a = warp_sum(a); b = warp_sum(b); c = warp_sum(c);
+    if ((threadIdx.x & 31) == 0) {
+        float* o = block_out + 3 * (threadIdx.x >> 5);
+        o[0] = a; o[1] = b; o[2] = c;
+    }
+}
+constexpr int VEC_PARTS = BX / 32;      // partial triples per block of a vectorised kernel
+
 // The fused step: one launch = one reference time step (src/main.cu:96-114) for every node it covers.
 // Scalar form, one cell per thread.  Two launch shapes: the whole slab (grid = segments x rows; used when nx is not a
 // multiple of 4) or only the "general" segments listed in p.gen_list (grid.x = number of listed segments), the
@@ -392,7 +403,7 @@ __global__ void __launch_bounds__(BX, vec_min_blocks(COLL, ODD)) step_vec_kernel
         float2 rho4[2], ux4[2], uy4[2];
         AdapterAvg av{};
 #if LBM_AVG_EARLY
-        if (COLL == C_CMOPT) { av.inv_rho = 1.0f / avg_raw[0]; av.inv_j = 1.0f / avg_raw[1]; av.inv_pi = 1.0f / avg_raw[2]; }
+        if (COLL == C_CMOPT) { av.inv_rho = fast_rcp(avg_raw[0]); av.inv_j = fast_rcp(avg_raw[1]); av.inv_pi = fast_rcp(avg_raw[2]); }
 #else
         if (COLL == C_CMOPT) av = load_adapter_avg(p.avg);
 #endif
@@ -443,7 +454,7 @@ __global__ void __launch_bounds__(BX, vec_min_blocks(COLL, ODD)) step_vec_kernel
             }
         }
     }
-    if (COLL == C_CMOPT && p.partials) block_partials(s0, s1, s2, p.partials + 3 * ((long long)blockIdx.y * gridDim.x + blockIdx.x));
+    if (COLL == C_CMOPT && p.partials) warp_partials(s0, s1, s2, p.partials + 3 * VEC_PARTS * ((long long)blockIdx.y * gridDim.x + blockIdx.x));
 }
 
 // ------------------------------------------------------------------ odd (neighbour) phase, lane-interleaved cells
@@ -510,7 +521,7 @@ __global__ void __launch_bounds__(BX, COLL == 3 ? LBM_ODD_MIN_BLOCKS_OPT : LBM_O
         }
         float2 rho4[2], ux4[2], uy4[2];
         AdapterAvg av{};
-        if (COLL == C_CMOPT) { av.inv_rho = 1.0f / avg_raw[0]; av.inv_j = 1.0f / avg_raw[1]; av.inv_pi = 1.0f / avg_raw[2]; }
+        if (COLL == C_CMOPT) { av.inv_rho = fast_rcp(avg_raw[0]); av.inv_j = fast_rcp(avg_raw[1]); av.inv_pi = fast_rcp(avg_raw[2]); }
         const Relax rx = relax_of(p);
         const bool forced = p.fx != 0.0f || p.fy != 0.0f;
         const V2 Fx = splat<V2>(p.fx), Fy = splat<V2>(p.fy);
@@ -559,7 +570,7 @@ __global__ void __launch_bounds__(BX, COLL == 3 ? LBM_ODD_MIN_BLOCKS_OPT : LBM_O
             if (k3) r[d3] = g[1][q].a.y;
         }
     }
-    if (COLL == C_CMOPT && p.partials) block_partials(s0, s1, s2, p.partials + 3 * ((long long)blockIdx.y * gridDim.x + blockIdx.x));
+    if (COLL == C_CMOPT && p.partials) warp_partials(s0, s1, s2, p.partials + 3 * VEC_PARTS * ((long long)blockIdx.y * gridDim.x + blockIdx.x));
 }
 
 // moments pre-pass for LBM_ADAPTER_EXACT: the grid sums of the CURRENT post-stream state, before any cell collides.
@@ -598,7 +609,7 @@ __global__ void __launch_bounds__(BX, 6) moments_vec_kernel(const Params p) {
         }
         if (c.act) { s0 = hsum(acc0); s1 = hsum(acc1); s2 = hsum(acc2); }
     }
-    block_partials(s0, s1, s2, p.partials + 3 * ((long long)blockIdx.y * gridDim.x + blockIdx.x));
+    warp_partials(s0, s1, s2, p.partials + 3 * VEC_PARTS * ((long long)blockIdx.y * gridDim.x + blockIdx.x));
 }
 
 // deterministic two-level reduction of the block partials: stage 1 (many blocks) folds the fp32 partials into
@@ -609,6 +620,7 @@ __device__ __forceinline__ void block_sum3(const T* in, long long n, long long s
     __shared__ double sm[3][256];
     double a = 0.0, b = 0.0, c = 0.0;
     for (long long i = start; i < n; i += stride) { a += (double)in[3 * i]; b += (double)in[3 * i + 1]; c += (double)in[3 * i + 2]; }
+    __syncthreads();                    // a second call in the same block must not overwrite sm while the first result is still being read
     sm[0][threadIdx.x] = a; sm[1][threadIdx.x] = b; sm[2][threadIdx.x] = c;
     __syncthreads();
     for (int s = 128; s > 0; s >>= 1) {
@@ -616,11 +628,6 @@ __device__ __forceinline__ void block_sum3(const T* in, long long n, long long s
         __syncthreads();
     }
     out[0] = sm[0][0]; out[1] = sm[1][0]; out[2] = sm[2][0];
-}
-__global__ void __launch_bounds__(256) reduce_stage1_kernel(const float* partials, long long nblocks, double* stage) {
-    double o[3];
-    block_sum3(partials, nblocks, (long long)blockIdx.x * 256 + threadIdx.x, (long long)gridDim.x * 256, o);
-    if (threadIdx.x < 3) stage[3 * blockIdx.x + threadIdx.x] = o[threadIdx.x];
 }
 // ---- what a slab knows about the other slabs of the decomposition (device-resident table, built at lbm_peer_attach*):
 // every slab's adapter mailbox, IBM node mailbox and IBM stage counters, reached over NVLink peer mappings (own entries included).
@@ -633,13 +640,25 @@ struct SlabNet {
     unsigned long long* ibm_stage[MAX_WORLD];   // [MAX_WORLD] IBM stage counters per slab, indexed by source rank
 };
 
-// stage 2 of the reduction; with `net` it also PUBLISHES this slab's sums for step `tag` into every slab's adapter mailbox
-// (one 32-byte store per slab over NVLink, data first, tag after a system-wide fence) — the send half of the device-side
-// all-reduce of CM<2,OptimalAdapter>'s grid sums (macroscopics.cuh:161-177 is a single-GPU atomicAdd + symbol copy)
-__global__ void __launch_bounds__(256) reduce_stage2_kernel(const double* stage, int n, double* sums, float* avg, double inv_n, int write_avg,
-                                                            const SlabNet* net, unsigned long long tag) {
+// The whole reduction in ONE launch: every block folds its share of the fp32 partials into an fp64 triple (stage[block]); the block
+// that arrives last (ticket) adds the triples in block order — a fixed order, so the result does not depend on which block that is —
+// and writes sums[3] and, on a single slab, avg[3] = sums / (NX*NY).  With `net` it also PUBLISHES this slab's sums for step `tag` into
+// every slab's adapter mailbox (one 32-byte store per slab over NVLink, data first, tag after a system-wide fence): the send half of the
+// device-side all-reduce of CM<2,OptimalAdapter>'s grid sums (macroscopics.cuh:161-177 is a single-GPU atomicAdd + symbol copy).
+__global__ void __launch_bounds__(256) reduce_kernel(const float* partials, long long nparts, double* stage, unsigned* ticket, double* sums, float* avg,
+                                                     double inv_n, int write_avg, const SlabNet* net, unsigned long long tag) {
+    __shared__ bool last;
     double o[3];
-    block_sum3(stage, n, threadIdx.x, 256, o);
+    block_sum3(partials, nparts, (long long)blockIdx.x * 256 + threadIdx.x, (long long)gridDim.x * 256, o);
+    if (threadIdx.x < 3) stage[3 * blockIdx.x + threadIdx.x] = o[threadIdx.x];
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    block_sum3((const volatile double*)stage, (long long)gridDim.x, (long long)threadIdx.x, 256ll, o);
+    if (threadIdx.x == 0) *ticket = 0u;
     if (threadIdx.x < 3) {
         sums[threadIdx.x] = o[threadIdx.x];
         if (write_avg) avg[threadIdx.x] = (float)(o[threadIdx.x] * inv_n);

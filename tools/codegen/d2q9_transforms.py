@@ -192,17 +192,18 @@ def cm_backward_chain(k, vx, vy):
 def bgk_chain(g, r, vx, vy, gx, gy, om, forced):
     """collide_bgk_v / bgk_pair"""
     onem, k = 1 - om, 1 - sp.Rational(1, 2) * om
-    c1 = fma(fma(vx, vx, vy * vy), sp.Rational(-3, 2), 1)
+    m15usq = fma(vx, vx, vy * vy) * sp.Rational(-3, 2)
     orho = r * om
     m3uF = fma(vx, gx, vy * gy) * -3 if forced else 0
     out = list(g)
-    s = (orho * sp.Rational(4, 9)) * c1
+    orw0 = orho * sp.Rational(4, 9)
+    s = fma(orw0, m15usq, orw0)
     if forced:
         s = fma(m3uF, sp.Rational(4, 9) * k, s)
     out[0] = fma(g[0], onem, s)
 
     def pair(qa, qb, cu, cF, orw, w):
-        sym = orw * fma(cu * sp.Rational(9, 2), cu, c1)
+        sym = fma(orw, fma(cu * sp.Rational(9, 2), cu, m15usq), orw)
         anti = (orw * 3) * cu
         if forced:
             sym = fma(fma(cu * 9, cF, m3uF), w * k, sym)
