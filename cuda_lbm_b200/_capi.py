@@ -27,7 +27,7 @@ SYMBOLS = [
     "lbm_set_populations", "lbm_get_populations", "lbm_step", "lbm_step_with_macroscopics", "lbm_sync",
     "lbm_get_macroscopics", "lbm_get_macroscopics_device", "lbm_reserve_macroscopics", "lbm_total_mass", "lbm_moment_avg", "lbm_adapter_prepass",
     "lbm_set_moment_sums", "lbm_get_moment_sums", "lbm_info", "lbm_next_step_needs_halo", "lbm_halo_pack_pre",
-    "lbm_halo_unpack_pre", "lbm_halo_pack_post", "lbm_halo_unpack_post", "lbm_peer_export", "lbm_peer_attach", "lbm_peer_attach_all", "lbm_peer_detach",
+    "lbm_halo_unpack_pre", "lbm_halo_pack_post", "lbm_halo_unpack_post", "lbm_peer_export", "lbm_peer_attach", "lbm_peer_attach_all", "lbm_peer_detach", "lbm_set_lookahead",
     "lbm_host_alloc", "lbm_host_free",
     "lbm_velocity_error_sums", "lbm_taylor_green_error_sums", "lbm_row_mean_velocity", "lbm_sample_velocity",
     "lbm_checkpoint_bytes", "lbm_checkpoint_write", "lbm_checkpoint_read",
@@ -108,6 +108,7 @@ def lib():
         "lbm_peer_attach": [vp, C.c_int, vp],
         "lbm_peer_attach_all": [vp, vp, C.c_int32],
         "lbm_peer_detach": [vp],
+        "lbm_set_lookahead": [vp, C.c_int32],
         "lbm_host_alloc": [C.POINTER(vp), C.c_int64],
         "lbm_host_free": [vp],
         "lbm_velocity_error_sums": [vp, vp, dp],

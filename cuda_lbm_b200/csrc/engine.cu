@@ -55,10 +55,13 @@ struct lbm_handle {
     struct StepGraph { cudaGraphExec_t exec = nullptr; std::string key; long long launches = 0; int d_avg = 0, d_pre = 0, d_nbrg = 0; } graph[2];
     int graph_mode = -1;            // LBM_B200_GRAPH: 0 never, 1 whenever possible, unset = slabs of up to 2^22 cells
     cudaEvent_t ev_bridge[2] = {nullptr, nullptr};
-    // peer-mapped slabs: lbm_step(h, n) keeps at most 3 x 8 steps enqueued ahead of the device (events recorded every 8 steps, the
-    // host waits for the one of 24 steps ago).  Deeper queues gain nothing, and when several slabs share ONE device (tests, more slabs
-    // than GPUs) their blocked launches exhaust the context's launch queue while the slab they wait for cannot enqueue any more.
+    // lbm_set_lookahead: lbm_step(h, n) on a peer-mapped slab keeps at most 3 x 8 steps enqueued ahead of the device (events recorded
+    // every 8 steps, the host waits for the one of 24 steps ago).  For callers that drive every slab from its own thread: when several
+    // slabs share ONE device (more slabs than GPUs) their blocked launches otherwise exhaust the context's launch queue while the slab
+    // they wait for cannot enqueue any more (seen with 4 slabs x 60 steps on one B200).  Off by default: a caller that enqueues the
+    // slabs one after the other from a single thread needs the unbounded queue.
     cudaEvent_t ev_throttle[3] = {nullptr, nullptr, nullptr};
+    bool bounded_lookahead = false;
     // lbm_run_from_host: copy streams and per-band events of the time-skewed pipeline (engine_pipeline.inc)
     cudaStream_t copy_in = nullptr, copy_out = nullptr; cudaEvent_t ev_pipe = nullptr; std::vector<cudaEvent_t> ev_band;
     unsigned long long pipe_epoch = 0;           // number of pipelined calls on several slabs (tags the level counters)      // legacy / per-thread user stream <-> own stream around graph replays
@@ -448,6 +451,12 @@ extern "C" int lbm_set_moment_sums(lbm_handle* h, const double s[3]) {
     sums_to_avg_kernel<<<1, 32, 0, h->stream>>>(h->sums, h->avg, 1.0 / ((double)h->cfg.nx * (double)h->cfg.ny));
     h->launches++;
     h->avg_for_ts = h->timestep + 1;
+    return LBM_OK;
+}
+
+extern "C" int lbm_set_lookahead(lbm_handle* h, int32_t bounded) {
+    if (!h) return fail(LBM_ERR_INVALID, "NULL handle");
+    h->bounded_lookahead = bounded != 0;
     return LBM_OK;
 }
 

@@ -378,7 +378,10 @@ public:
         } else {
             std::vector<unsigned char> descs((size_t)G * LBM_PEER_DESC_BYTES);
             for (int g = 0; g < G; g++) LBM_B200_CALL(lbm_peer_export(slabs[(size_t)g].h, descs.data() + (size_t)g * LBM_PEER_DESC_BYTES));
-            for (int g = 0; g < G; g++) LBM_B200_CALL(lbm_peer_attach_all(slabs[(size_t)g].h, descs.data(), G));
+            for (int g = 0; g < G; g++) {
+                LBM_B200_CALL(lbm_peer_attach_all(slabs[(size_t)g].h, descs.data(), G));
+                LBM_B200_CALL(lbm_set_lookahead(slabs[(size_t)g].h, 1));       // every slab has its own host thread here, and slabs may share a device
+            }
             std::cout << "[LBM]: " << G << " y-slabs on " << std::min(G, ndev) << " GPU(s), peer-mapped\n";
         }
         checkCudaErrors(cudaSetDevice(home_device));

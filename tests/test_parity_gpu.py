@@ -72,7 +72,10 @@ def test_mass_conservation_fixed_physics():
     e.step(500)
     m1 = e.total_mass()
     e.close()
-    assert abs(m1 / m0 - 1.0) < 2e-6, (m0, m1)
+    # "round-off" includes a systematic part the reference shares: its fp32 lattice weights add up to 1 + 7.45e-9 (4/9, 1/9, 1/36 rounded to
+    # float), and at omega = 1 every step replaces f by f_eq = w rho (...): +7.45e-9 per step, 3.7e-6 after 500 (SURVEY.md 8c measured
+    # +7e-6 per 1000 steps for the reference's arithmetic).  Measured here: 2.9e-6.
+    assert abs(m1 / m0 - 1.0) < 5e-6, (m0, m1)
 
 
 def test_lagged_adapter_close_to_exact():
