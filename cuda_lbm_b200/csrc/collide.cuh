@@ -127,15 +127,20 @@ LBM_HD void collide_mrt_v(const Relax& r, V g[Q], V rho, V ux, V uy, bool forced
     m[7] = a13 - a24;
     m[8] = a57 - a68;
     const V jx = rho * ux, jy = rho * uy, usq = fma(ux, ux, uy * uy);
-    V me[Q];
-    me[0] = rho;
-    me[1] = rho * fma(usq, 3.0f, -2.0f);
-    me[2] = rho * fma(usq, -3.0f, 1.0f);
-    me[3] = jx; me[4] = -jx; me[5] = jy; me[6] = -jy;
-    me[7] = fma(jx, ux, -(jy * uy));
-    me[8] = jx * uy;
+    // d = m_eq - m with m_eq = (rho, rho (3 u^2 - 2), rho (1 - 3 u^2), jx, -jx, jy, -jy, jx ux - jy uy, jx uy).  Every product that
+    // feeds the subtraction is written as ONE FMA: ptxas contracts a single-use packed product into a following packed add even
+    // though both carry .rn (mul.rn.f32x2 + add.rn.f32x2 -> FFMA2; it never does so for the scalar forms), which made a cell's
+    // result depend on whether the one-cell or the two-cell instantiation computed it (tools/v1v2_probe.cu).
+    V d[Q];
+    d[0] = rho - m[0];
+    d[1] = fma(rho, fma(usq, 3.0f, -2.0f), -m[1]);
+    d[2] = fma(rho, fma(usq, -3.0f, 1.0f), -m[2]);
+    d[3] = fma(rho, ux, -m[3]); d[4] = fma(-rho, ux, -m[4]);
+    d[5] = fma(rho, uy, -m[5]); d[6] = fma(-rho, uy, -m[6]);
+    d[7] = fma(jx, ux, -(jy * uy)) - m[7];
+    d[8] = fma(jx, uy, -m[8]);
 LBM_UNROLL
-    for (int i = 0; i < Q; i++) m[i] = fma(me[i] - m[i], r.S[i], m[i]);
+    for (int i = 0; i < Q; i++) m[i] = fma(d[i], r.S[i], m[i]);
     if (forced) {
         const V uF = fma(Fx, ux, Fy * uy);
         V F[Q];

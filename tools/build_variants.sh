@@ -8,6 +8,6 @@ ARCH="-gencode arch=compute_100a,code=sm_100a"
 while [ $# -ge 2 ]; do
     name=$1; flags=$2; shift 2
     mkdir -p tools/variants/$name
-    ( nvcc $ARCH -O3 -lineinfo --std=c++17 -Xcompiler -fPIC $flags -shared -o tools/variants/$name/liblbm_b200.so cuda_lbm_b200/csrc/engine.cu -lcudart && echo "built $name ($flags)" ) &
+    ( nvcc $ARCH -O3 -lineinfo --std=c++17 -fmad=false -Xcompiler -fPIC $flags -shared -o tools/variants/$name/liblbm_b200.so cuda_lbm_b200/csrc/engine.cu -lcudart && echo "built $name ($flags)" ) &
 done
 wait
