@@ -61,6 +61,11 @@ struct Params {
     // bottom edge row, addressed as peer[s] + plane * peer_plane[s] + peer_off[s] + x.  nullptr = use this slab's ghost rows.
     float* peer[2]; long long peer_plane[2]; long long peer_off[2];
     long long plane;        // floats per slot plane of this slab: A[q] == A[0] + q * plane
+    // CM<2,OptimalAdapter>, exact grid sums without a pre-pass ("trailing moments", kernels.cuh): rows `trail` behind the row a block
+    // collides, the same block sums the post-stream moments of step t + 1 out of L2.  rowdone[(t & 1) * nyl + y] counts the warps of
+    // row y that have stored their cells in step t; mclass[segment]: 0 = sum every cell here, 1 = skip cells that are general or touch a
+    // general cell (the host sums those from a list after the step), 2 = nothing to sum here.
+    int trail; unsigned* rowdone; const uint8_t* mclass; int* trail_err;
 };
 constexpr int SEG = 128;
 

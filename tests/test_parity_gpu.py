@@ -431,19 +431,24 @@ def test_run_from_host_on_peer_mapped_slabs(nx, ny, world, coll, nsteps):
 
 
 # ---------------------------------------------------------------- rows of whole 128-cell segments: lane-interleaved odd kernel, mixed segments
-def _steps_fields(case, nsteps, quirks=63, adapter_mode=0, odd_kernel=True):
+def _steps_fields(case, nsteps, quirks=63, adapter_mode=0, odd_kernel=True, env=None, chunks=None):
     import os
-    old = os.environ.get("LBM_B200_ODD")
-    os.environ["LBM_B200_ODD"] = "1" if odd_kernel else "0"       # read by lbm_create
+    env = dict(env or {}, LBM_B200_ODD="1" if odd_kernel else "0")       # read by lbm_create
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
     try:
         e = make_engine(case, quirks, adapter_mode)
     finally:
-        if old is None:
-            del os.environ["LBM_B200_ODD"]
-        else:
-            os.environ["LBM_B200_ODD"] = old
+        for k, v in old.items():
+            if v is None:
+                del os.environ[k]
+            else:
+                os.environ[k] = v
     e.init_fields(*case.init_fields())
-    e.step(nsteps, macroscopics=True)
+    for c in (chunks or [nsteps])[:-1]:
+        e.step(c)
+    e.step((chunks or [nsteps])[-1], macroscopics=True)
+    e.sync()
     out = e.macroscopics(), e.populations(), e.info()
     e.close()
     return out
@@ -507,3 +512,36 @@ def test_lagged_adapter_with_mixed_segments():
     (rho_t, u_t), f_t, _ = _steps_fields(case, 12, adapter_mode=1, odd_kernel=True)
     (rho_s, u_s), f_s, _ = _steps_fields(case, 12, adapter_mode=1, odd_kernel=False)
     assert np.isfinite(f_t).all() and np.abs(f_t - f_s).max() <= 1e-6, float(np.abs(f_t - f_s).max())
+
+
+TRAIL_CASES = [("tg", 512, 40, (True, True)), ("tg", 128, 300, (True, True)), ("lid", 384, 40, (False, False)), ("cyl_ibm", 512, 48, (False, False)),
+               ("pois", 256, 24, (True, False)), ("cyl_flag", 256, 64, (False, False))]
+
+
+@pytest.mark.parametrize("kind,nx,ny,periodic", TRAIL_CASES)
+@pytest.mark.parametrize("rows", [0, 2, 5])
+def test_trailing_moments_equal_the_moments_prepass(kind, nx, ny, periodic, rows):
+    """CM<2,OptimalAdapter>, LBM_ADAPTER_EXACT: the grid sums of step t + 1 taken by the step kernels of step t out of L2, `rows` rows
+    behind the rows they collide (0 = the engine's choice), plus the list pass for general cells and their neighbours, against the
+    moments pre-pass (LBM_B200_TRAIL=0).  Same sums up to fp32 / fp64 summation order: fields agree to 1e-6 after 28 steps (as in the lagged-adapter test); both stay within the usual
+    bounds of the CPU oracle.  Steps are cut into calls so that plain launches, the step that leads into the steady state and CUDA-graph
+    replays (16 steps each) all occur, with periodic wrap, walls (neighbour-reading corner BCs), flag bodies, IBM bodies and a force."""
+    nu = 1.0 / 6.0 if kind in ("tg", "pois") else (0.03 if kind == "lid" else float(cases._cyl_nu(ny)))
+    um = {"tg": 0.04, "pois": 0.05, "lid": 0.1}.get(kind, 0.05)
+    force = cases._pois_force(ny) if kind == "pois" else (0.0, 0.0)
+    case = cases.Case(f"trail_{kind}_{nx}x{ny}", nx, ny, cases.CM_OPT, nu, periodic, um, kind, force=force, np_markers=24, scale=nx // 128)
+    chunks = [3, 20, 1, 4]
+    n = sum(chunks)
+    env_t = {"LBM_B200_TRAIL": "1", "LBM_B200_GRAPH": "1"}
+    if rows:
+        env_t["LBM_B200_TRAIL_ROWS"] = str(rows)
+    (rho_t, u_t), f_t, info_t = _steps_fields(case, n, env=env_t, chunks=chunks)
+    (rho_s, u_s), f_s, info_s = _steps_fields(case, n, env={"LBM_B200_TRAIL": "0", "LBM_B200_GRAPH": "1"}, chunks=chunks)
+    assert np.isfinite(f_t).all()
+    assert info_t.kernel_launches < info_s.kernel_launches          # no moments_vec_kernel in the steady state
+    assert np.abs(f_t - f_s).max() <= 1e-6 and np.abs(rho_t - rho_s).max() <= 2e-6 and np.abs(u_t - u_s).max() <= 1e-6, float(np.abs(f_t - f_s).max())
+    o = make_oracle(case)
+    o.init(*case.init_fields())
+    o.step(n)
+    assert np.abs(f_t - o.populations()).max() <= TOL_F * n ** 0.5
+    assert np.abs(rho_t - o.macroscopics()[0]).max() <= TOL_RHO * n ** 0.5
