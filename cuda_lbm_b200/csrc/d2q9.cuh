@@ -56,16 +56,16 @@ struct Params {
     // the vectorised kernels skip exactly the general cells.  The general (scalar) kernel is launched over the segments listed in
     // gen_list (type 1) and over the cells listed in gen_cells (the general cells of type-2 segments, local node ids).
     const uint8_t* segmask; int nsx; const int* gen_list;
+    // rows [pure_y0, pure_y1) x segments [pure_s0, pure_s1): a rectangle in which EVERY segment is class 0 (the largest one, found on the
+    // host).  A warp inside it does not read segmask at all: waiting for that byte before it requests its populations made every warp
+    // live one L2 round trip longer (the cavity's vector kernels ran at 219 / 249 us against 197 / 213 us for the same operator on
+    // the periodic box), and ptxas moves the test in front of the loads however the source orders them.
+    int pure_y0, pure_y1, pure_s0, pure_s1;
     const long long* gen_cells; long long gen_cell_count;
     // direct y-slab coupling over NVLink peer memory: [0] = the lower neighbour's top edge row, [1] = the upper neighbour's
     // bottom edge row, addressed as peer[s] + plane * peer_plane[s] + peer_off[s] + x.  nullptr = use this slab's ghost rows.
     float* peer[2]; long long peer_plane[2]; long long peer_off[2];
     long long plane;        // floats per slot plane of this slab: A[q] == A[0] + q * plane
-    // CM<2,OptimalAdapter>, exact grid sums without a pre-pass ("trailing moments", kernels.cuh): rows `trail` behind the row a block
-    // collides, the same block sums the post-stream moments of step t + 1 out of L2.  rowdone[(t & 1) * nyl + y] counts the warps of
-    // row y that have stored their cells in step t; mclass[segment]: 0 = sum every cell here, 1 = skip cells that are general or touch a
-    // general cell (the host sums those from a list after the step), 2 = nothing to sum here.
-    int trail; unsigned* rowdone; const uint8_t* mclass; int* trail_err;
 };
 constexpr int SEG = 128;
 

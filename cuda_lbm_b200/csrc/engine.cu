@@ -93,12 +93,7 @@ struct lbm_handle {
     // general-path segments (kernels.cuh): mask per 128-cell segment + compact list, rebuilt lazily
     uint8_t* segmask = nullptr; int* gen_list = nullptr; int gen_count = 0; int nsx = 0; bool segs_dirty = true;
     long long* gen_cells = nullptr; long long gen_cell_count = 0, gen_cell_cap = 0;      // general cells of the mixed segments (local node ids)
-    // CM<2,OptimalAdapter>, exact sums without a pre-pass (trailing moments, kernels.cuh): per-row completion counters of both step
-    // parities, segment classes, the cells left to the list pass (general cells and their neighbours)
-    bool trail_enabled = true; int trail_rows_env = 0; int sm_count = 148;
-    unsigned* rowdone = nullptr; int* trail_err = nullptr; uint8_t* mclass = nullptr; bool trail_dirty = true;
-    long long* mom_cells = nullptr; long long mom_cell_count = 0, mom_cell_cap = 0;
-    int trail_last_ts = -2;         // last step that ran with trailing moments (its successor finds the counters ready)
+    int pure[4] = {0, 0, 0, 0};     // rows [0],[1]) x segments [2],[3]): the largest rectangle of all-vector segments (Params::pure_*)
     // adapter
     float* partials = nullptr; long long n_partials = 0; double* stage = nullptr; double* sums = nullptr; float* avg = nullptr; int avg_for_ts = -1; int pre_for_ts = -1;
     // macroscopics
@@ -165,8 +160,8 @@ static Params make_params(lbm_handle* h, int t) {
     p.nbr_nodes = h->nbr_nodes; p.nbr_g = h->nbr_g; p.nbr_count = h->nbr_count;
     p.ibm_nodes = h->ibm_nodes; p.ibm_force = h->ibm_force; p.ibm_count = h->ibm_count;
     p.avg = h->avg; p.partials = nullptr; p.rho_out = nullptr; p.u_out = nullptr;
+    p.pure_y0 = h->pure[0]; p.pure_y1 = h->pure[1]; p.pure_s0 = h->pure[2]; p.pure_s1 = h->pure[3];
     p.segmask = nullptr; p.nsx = h->nsx; p.gen_list = nullptr; p.gen_cells = nullptr; p.gen_cell_count = 0; p.plane = (long long)h->plane;
-    p.trail = 0; p.rowdone = nullptr; p.mclass = nullptr; p.trail_err = nullptr;
     for (int sd = 0; sd < 2; sd++) { p.peer[sd] = h->peer[sd].attached ? h->peer[sd].base : nullptr; p.peer_plane[sd] = h->peer[sd].plane; p.peer_off[sd] = h->peer[sd].off; }
     return p;
 }
@@ -194,7 +189,7 @@ static void preload_kernels(int device) {
     preload(nbr_gather_kernel<false>); preload(nbr_gather_kernel<true>);
     preload(ibm_kernel<false>); preload(ibm_kernel<true>); preload(ibm_state_kernel<false>); preload(ibm_state_kernel<true>);
     preload(ibm_markers_kernel); preload(ibm_nodes_kernel); preload(ibm_gather_kernel<false>); preload(ibm_gather_kernel<true>); preload(ibm_solve_kernel);
-    preload(wait_neighbours_kernel); preload(signal_neighbours_kernel); preload(build_segmask_kernel); preload(build_mclass_kernel);
+    preload(wait_neighbours_kernel); preload(signal_neighbours_kernel); preload(build_segmask_kernel);
     preload(init_fields_kernel); preload(init_taylor_green_kernel);
     cudaGetLastError();
 }
@@ -224,7 +219,7 @@ extern "C" int lbm_destroy(lbm_handle* h) {
     for (auto& m : h->mapped) if (m.ipc_base) cudaIpcCloseMemHandle(m.ipc_base);
     void* ptrs[] = {h->d_net, h->sync_timeout, h->pop, h->flags, h->force_plane, h->ring, h->nbr_nodes, h->nbr_src, h->nbr_g, h->d_pts, h->ibm_nodes,
                     h->sten_idx, h->sten_w, h->csr_row, h->csr_k, h->csr_w, h->ibm_rho, h->ibm_uprev, h->ibm_lagF, h->ibm_force, h->ibm_mail_idx, h->d_utarget,
-                    h->partials, h->stage, h->sums, h->avg, h->rho_out, h->u_out, h->mass_acc, h->segmask, h->gen_list, h->gen_cells, h->val_stage, h->rowdone, h->mclass, h->mom_cells};
+                    h->partials, h->stage, h->sums, h->avg, h->rho_out, h->u_out, h->mass_acc, h->segmask, h->gen_list, h->gen_cells, h->val_stage};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     for (auto& g : h->graph) if (g.exec) cudaGraphExecDestroy(g.exec);
@@ -306,9 +301,6 @@ extern "C" int lbm_create(const lbm_config* cfg, lbm_handle** out) {
     cudaMemsetAsync(h->d_net, 0, sizeof(SlabNet), h->stream);
     cudaMemsetAsync(h->ring, 0, (size_t)2 * h->perim * Q * sizeof(float), h->stream);
     if (const char* v = getenv("LBM_B200_ODD")) h->odd_interleaved = v[0] != '0';
-    if (const char* v = getenv("LBM_B200_TRAIL")) h->trail_enabled = v[0] != '0';          // 0: exact adapter sums by the moments pre-pass
-    if (const char* v = getenv("LBM_B200_TRAIL_ROWS")) h->trail_rows_env = atoi(v);        // distance of the trailing moments in rows
-    { int n = 0; if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, cfg->device) == cudaSuccess && n > 0) h->sm_count = n; }
     float one[3] = {1.f, 1.f, 1.f};
     cudaMemcpyAsync(h->avg, one, sizeof(one), cudaMemcpyHostToDevice, h->stream);
     cudaStreamSynchronize(h->stream);
@@ -337,12 +329,7 @@ static int rebuild_ibm(lbm_handle* h);
 // peer-mapped slabs stepping from several host threads, a cudaMalloc (a device-wide synchronisation) issued by one slab's first step
 // while another slab's handshake kernel already spins for it would dead-lock until the handshake timeout.
 static int prepare_resources(lbm_handle* h, bool want_macros);
-static bool trail_on(const lbm_handle* h);
-static int settle(lbm_handle* h) {
-    // trailing moments: the sums for the next step were taken with the configuration as it was — take them again by the pre-pass
-    if (trail_on(h)) h->avg_for_ts = -1;
-    return h->direct() ? prepare_resources(h, false) : LBM_OK;
-}
+static int settle(lbm_handle* h) { return h->direct() ? prepare_resources(h, false) : LBM_OK; }
 
 extern "C" int lbm_set_flags(lbm_handle* h, const int32_t* flags) {
     if (!h || !flags) return fail(LBM_ERR_INVALID, "NULL argument");
@@ -397,7 +384,7 @@ extern "C" int lbm_set_flags(lbm_handle* h, const int32_t* flags) {
         CU(cudaMemcpyAsync(h->nbr_src, b.data(), b.size() * 8, cudaMemcpyHostToDevice, h->stream));
         CU(cudaStreamSynchronize(h->stream));
     }
-    h->segs_dirty = true; h->trail_dirty = true;
+    h->segs_dirty = true;
     if (!h->h_pts.empty()) return rebuild_ibm(h);       // re-mark the IBM bit
     return settle(h);
 }
@@ -405,7 +392,6 @@ extern "C" int lbm_set_flags(lbm_handle* h, const int32_t* flags) {
 extern "C" int lbm_set_body_force(lbm_handle* h, float fx, float fy) {
     if (!h) return fail(LBM_ERR_INVALID, "NULL handle");
     h->cfg.force_x = fx; h->cfg.force_y = fy;
-    if (trail_on(h)) h->avg_for_ts = -1;
     return LBM_OK;
 }
 
@@ -415,10 +401,10 @@ extern "C" int lbm_set_force_field(lbm_handle* h, const float* force_aos) {
     // h->stream is a non-blocking stream: order the update after the steps an asynchronous lbm_step has enqueued on it
     CU(cudaStreamSynchronize(h->stream));
     if (!force_aos) {
-        if (h->force_plane) { cudaFree(h->force_plane); h->bytes -= (long long)h->nloc * (long long)sizeof(float2); h->force_plane = nullptr; h->segs_dirty = true; h->trail_dirty = true; }
+        if (h->force_plane) { cudaFree(h->force_plane); h->bytes -= (long long)h->nloc * (long long)sizeof(float2); h->force_plane = nullptr; h->segs_dirty = true; }
         return settle(h);
     }
-    if (!h->force_plane) { CU(dmalloc(h, &h->force_plane, (size_t)h->nloc)); h->segs_dirty = true; h->trail_dirty = true; }
+    if (!h->force_plane) { CU(dmalloc(h, &h->force_plane, (size_t)h->nloc)); h->segs_dirty = true; }
     CU(cudaMemcpyAsync(h->force_plane, force_aos + (size_t)2 * h->y0 * h->cfg.nx, (size_t)h->nloc * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return settle(h);
@@ -427,7 +413,7 @@ extern "C" int lbm_set_force_field(lbm_handle* h, const float* force_aos) {
 extern "C" int lbm_set_force_field_device(lbm_handle* h, const float* d_force) {
     if (!h || !d_force) return fail(LBM_ERR_INVALID, "NULL argument");
     CU(cudaSetDevice(h->cfg.device));
-    if (!h->force_plane) { CU(cudaStreamSynchronize(h->stream)); CU(dmalloc(h, &h->force_plane, (size_t)h->nloc)); h->segs_dirty = true; h->trail_dirty = true; }
+    if (!h->force_plane) { CU(cudaStreamSynchronize(h->stream)); CU(dmalloc(h, &h->force_plane, (size_t)h->nloc)); h->segs_dirty = true; }
     // stream-ordered behind the steps already enqueued; the caller's buffer may be reused once the call returns
     CU(cudaMemcpyAsync(h->force_plane, d_force, (size_t)h->nloc * sizeof(float2), cudaMemcpyDeviceToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));

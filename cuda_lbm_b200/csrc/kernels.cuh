@@ -199,6 +199,12 @@ __device__ __forceinline__ void st4(float* p, float a, float b, float c, float d
 #endif
 }
 
+// class of segment sx of row yl; no memory access inside the all-vector rectangle
+__device__ __forceinline__ uint8_t segment_class(const Params& p, int yl, int sx) {
+    if (!p.segmask || (yl >= p.pure_y0 && yl < p.pure_y1 && sx >= p.pure_s0 && sx < p.pure_s1)) return SEG_VEC;
+    return p.segmask[(long long)yl * p.nsx + sx];
+}
+
 // SEG_MIXED segments: bit k set = cell x0 + k of this thread belongs to the general kernel
 __device__ __forceinline__ unsigned skip_mask4(const Params& p, int x0, int yl) {
     unsigned m = 0;
@@ -256,7 +262,7 @@ __device__ __forceinline__ bool vec_setup(const Params& p, VecCtx& c) {
     const int xv = c.act ? xv_raw : nv - 1;           // idle lanes of the last warp shadow a valid cell (loads only)
     bool warp_on = (xv_raw & ~31) < nv;               // warp-uniform: one warp = one 128-cell segment
     uint8_t segtype = SEG_VEC;
-    if (warp_on && p.segmask) { segtype = p.segmask[(long long)c.yl * p.nsx + (xv_raw >> 5)]; warp_on = segtype != SEG_GENERAL; }
+    if (warp_on) { segtype = segment_class(p, c.yl, xv_raw >> 5); warp_on = segtype != SEG_GENERAL; }
     if (!warp_on) return false;
     c.x0 = xv << 2;
     c.skip = segtype == SEG_MIXED ? skip_mask4(p, c.x0, c.yl) : 0u;
@@ -320,141 +326,6 @@ __device__ __forceinline__ void vec_load(const Params& p, const VecCtx& c, V2 g[
     }
 }
 
-// ------------------------------------------------------------------ trailing moments (LBM_ADAPTER_EXACT without a pre-pass)
-// CM<2,OptimalAdapter> needs the grid sums of rho, rho|u|, |Pi| of the post-stream state of step t+1 before any cell collides in step
-// t+1 (CM.cuh:104-107).  Taken by a pre-pass they cost a second read of every population: +36 B per cell update on a path that moves
-// 72.  But what a cell pulls in step t+1 is exactly what its 3x3 neighbourhood stores in step t, and those lines are still in the
-// 126 MB L2 a few dozen rows behind the rows being collided.  So every warp of block row y of the step kernel also sums the t+1 moments
-// of its segment in row y - trail:
-//   * at its start, right behind its own population loads, it checks that rows y-trail-1 .. y-trail+1 are complete (rowdone counts the
-//     warps of a row that have stored and fenced; blocks are dispatched in row order, so whatever a warp waits for was started before
-//     it — and with trail = twice the rows in flight it practically never waits) and starts cp.async.cg copies (L2 -> shared memory,
-//     past L1, which may hold lines from before the neighbours' stores) of the nine slot rows of that segment: no registers held, and
-//     the L2 round trip hides behind the DRAM latency of its own loads;
-//   * after its own cells are stored it sums the moments out of shared memory, then fences and counts itself into rowdone[y].
-// DRAM sees 72 B per cell update again.  Cells the general kernel owns, and cells with such a neighbour (its stores are not counted),
-// are left out here: the host sums them from a list after the step (moments_kernel), O(perimeter + bodies).  Single slab only.
-constexpr int TRAIL_W = SEG + 8;                // one slot row of a segment in shared memory: cells x0 - 4 .. x0 + 131
-template <int COLL> struct TrailSmem { static constexpr int floats = COLL == C_CMOPT ? (BX / 32) * Q * TRAIL_W : 4; };
-struct TrailCtx { int ym; uint8_t mc; bool on; };
-
-__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* ptr) {      // LDG.STRONG.GPU + L1 invalidate: no wait for the loads in flight
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
-    return v;
-}
-__device__ __forceinline__ unsigned smem_addr(const void* ptr) { return (unsigned)__cvta_generic_to_shared(ptr); }
-// one bulk copy (the TMA engine: global -> shared through L2, past L1) that reports its bytes to the warp's mbarrier
-__device__ __forceinline__ void bulk_g2s(float* dst, const float* src, unsigned bytes, unsigned long long* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
-}
-// the cell is general, or a cell of its 3x3 neighbourhood is (y wraps inside the slab or ends at a domain edge: one slab)
-__device__ __forceinline__ bool trail_excluded(const Params& p, int x, int yl) {
-    for (int dy = -1; dy <= 1; dy++)
-        for (int dx = -1; dx <= 1; dx++) {
-            int xn = x, yn = yl;
-            if (!hop(p, xn, yn, dx, dy)) return true;
-            if (cell_is_general(p, xn, yn)) return true;
-        }
-    return false;
-}
-// Start of a warp of block row `by`, segment sx: which row it sums, wait until that row's neighbourhood is complete, start the copies.
-// NEXT_ODD: step t+1 is a neighbour (odd) step, g_q(x) = A[opp q][x - c_q]; otherwise g_q(x) = A[q][x].
-template <bool NEXT_ODD>
-__device__ __forceinline__ TrailCtx trail_begin(const Params& p, int by, int sx, int lane, float* buf, unsigned long long* bar) {
-    TrailCtx c;
-    c.ym = by - p.trail; c.mc = 0; c.on = false;
-    if (p.wrap_y) { if (c.ym == 0) return c; if (c.ym == p.nyl) c.ym = 0; }      // row 0 reads row nyl-1, the last to complete: it comes last
-    if (c.ym < 0 || c.ym >= p.nyl || sx >= p.nsx) return c;
-    if (p.mclass) c.mc = p.mclass[(long long)c.ym * p.nsx + sx];
-    if (c.mc == 2) return c;
-    c.on = true;
-    int ya = c.ym - 1, yb = c.ym + 1;
-    if (p.wrap_y) { if (ya < 0) ya += p.nyl; if (yb >= p.nyl) yb -= p.nyl; }
-    if (lane == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(bar)) : "memory");
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    {   // lanes 0..2 watch one row each (rows beyond a non-periodic edge are only read for excluded cells)
-        const int r = lane == 0 ? ya : (lane == 1 ? c.ym : yb);
-        const bool watch = lane < 3 && r >= 0 && r < p.nyl;
-        const unsigned* done = p.rowdone + (size_t)(p.t & 1) * p.nyl + (watch ? r : 0);
-        const unsigned need = gridDim.x * (blockDim.x >> 5);
-        if (__any_sync(FULL, watch && ld_acquire_u32(done) < need)) {          // practically never: the rows are `trail` rows behind
-            const long long t0 = clock64();
-            while (__any_sync(FULL, watch && ld_acquire_u32(done) < need)) {
-                if (clock64() - t0 > 4000000000ll) { if (lane == 0) *p.trail_err = 1; break; }      // ~2 s: never hang the device
-                __nanosleep(200);
-            }
-        }
-    }
-    // the rows were stored through the generic proxy by other SMs, the copies read them through the async proxy
-    asm volatile("fence.proxy.async.global;" ::: "memory");
-    __syncwarp();
-    const int x0 = sx * SEG;
-    const bool inner = x0 > 0 && x0 + SEG < p.nx;                               // the window x0 - 4 .. x0 + 131 is contiguous in memory
-    constexpr unsigned ROW_BYTES = (NEXT_ODD ? TRAIL_W : SEG) * 4;
-    if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(Q * ROW_BYTES) : "memory");
-    __syncwarp();
-    // lane q (< 9): the row of slot plane q; lanes 9 .. 26: the 16-byte ends of the window where it wraps around the row
-    const int q = lane < Q ? lane : (lane - Q) % Q;
-    const float* row;
-    {
-        const int sp = q == 0 ? 0 : (NEXT_ODD ? opp(q) : q);
-        const int sy = (NEXT_ODD && q > 0) ? (cy(q) > 0 ? ya : (cy(q) < 0 ? yb : c.ym)) : c.ym;
-        row = (q == 0 ? p.A0[(p.t + 1) & 1] : p.A[sp]) + rowoff(p, sy);
-    }
-    float* dst = buf + q * TRAIL_W;
-    if (!NEXT_ODD) { if (lane < Q) bulk_g2s(dst + 4, row + x0, SEG * 4, bar); }
-    else if (inner) { if (lane < Q) bulk_g2s(dst, row + x0 - 4, TRAIL_W * 4, bar); }
-    else if (lane < Q) bulk_g2s(dst + 4, row + x0, SEG * 4, bar);
-    else if (lane < 2 * Q) bulk_g2s(dst, row + (x0 == 0 ? p.nx - 4 : x0 - 4), 16, bar);
-    else if (lane < 3 * Q) bulk_g2s(dst + 4 + SEG, row + (x0 + SEG == p.nx ? 0 : x0 + SEG), 16, bar);
-    return c;
-}
-// End of the warp: sums of (rho, rho|u|, |Pi|) of the post-stream state of step t+1 over the segment, lane-interleaved like step_odd_kernel
-template <bool NEXT_ODD>
-__device__ __forceinline__ void trail_end(const Params& p, const TrailCtx& c, int sx, int lane, const float* buf, unsigned long long* bar, float& s0, float& s1, float& s2) {
-    if (!c.on) return;
-    {
-        unsigned ok = 0;
-        const unsigned ba = smem_addr(bar);
-        while (!ok) asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(ba) : "memory");
-    }
-    const int x = sx * SEG + lane;                                              // cells x, x + 32, x + 64, x + 96
-    unsigned skip = 0;
-    if (c.mc == 1) skip = (trail_excluded(p, x, c.ym) ? 1u : 0u) | (trail_excluded(p, x + 32, c.ym) ? 2u : 0u) | (trail_excluded(p, x + 64, c.ym) ? 4u : 0u) | (trail_excluded(p, x + 96, c.ym) ? 8u : 0u);
-    V2 g[2][Q];
-#pragma unroll
-    for (int q = 0; q < Q; q++) {
-        const float* r = buf + q * TRAIL_W + 4 + lane - (NEXT_ODD ? cx(q) : 0);
-        g[0][q].a.x = r[0]; g[0][q].a.y = r[32]; g[1][q].a.x = r[64]; g[1][q].a.y = r[96];
-    }
-    const bool forced = p.fx != 0.0f || p.fy != 0.0f;
-    V2 acc0 = splat<V2>(0.f), acc1 = acc0, acc2 = acc0;
-#pragma unroll
-    for (int hf = 0; hf < 2; hf++) {
-        const Mom<V2> m = moments_v(g[hf]);
-        V2 ux = m.ux, uy = m.uy;
-        if (forced) { const V2 hr = m.inv_rho * 0.5f; ux = fma(splat<V2>(p.fx), hr, ux); uy = fma(splat<V2>(p.fy), hr, uy); }
-        const bool z0 = (skip >> (2 * hf)) & 1u, z1 = (skip >> (2 * hf + 1)) & 1u;
-        acc0 = acc0 + zero_lanes(m.rho, z0, z1); acc1 = acc1 + zero_lanes(jmag_v(ux, uy, m.rho), z0, z1); acc2 = acc2 + zero_lanes(pi_norm_v(m), z0, z1);
-    }
-    s0 = hsum(acc0); s1 = hsum(acc1); s2 = hsum(acc2);
-}
-// a warp of block row `by` has stored its cells (or has none): publish (release: every store of the warp is in L2 before the count
-// moves), and clear the counter the NEXT step will count in
-__device__ __forceinline__ void trail_row_done(const Params& p, int by, int lane) {
-    if (by >= p.nyl) return;
-    __syncwarp();
-#ifdef LBM_TRAIL_NOFENCE       // timing experiment only: the count may overtake the stores
-    if (lane == 0) asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(p.rowdone + (size_t)(p.t & 1) * p.nyl + by) : "memory");
-#else
-    if (lane == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.rowdone + (size_t)(p.t & 1) * p.nyl + by) : "memory");
-#endif
-    if (blockIdx.x == 0 && threadIdx.x == 0) p.rowdone[(size_t)((p.t + 1) & 1) * p.nyl + by] = 0u;
-}
-
 // NOTE: setup and loads are written out inside this kernel on purpose.  Routing them through vec_setup / vec_load (as the
 // moments pre-pass does) is semantically identical but changed nvcc's schedule enough to cost 12 % on the odd phase
 // (5.80 vs 6.58 TB/s at 16384^2, profiles/r01_kbench_packed.txt), with the same register count.
@@ -466,16 +337,10 @@ __global__ void __launch_bounds__(BX, vec_min_blocks(COLL, ODD)) step_vec_kernel
     const int lane = threadIdx.x & 31;
     bool act = xv_raw < nv;
     const int xv = act ? xv_raw : nv - 1;             // idle lanes of the last warp shadow a valid cell (loads only)
-    const bool trail = COLL == C_CMOPT && !ODD && p.trail > 0;      // block rows beyond the slab only sum trailing moments
-    bool warp_on = (xv_raw & ~31) < nv && yl < p.nyl; // warp-uniform: one warp = one 128-cell segment
+    bool warp_on = (xv_raw & ~31) < nv;               // warp-uniform: one warp = one 128-cell segment
     uint8_t segtype = SEG_VEC;
-    if (warp_on && p.segmask) { segtype = p.segmask[(long long)yl * p.nsx + (xv_raw >> 5)]; warp_on = segtype != SEG_GENERAL; }
+    if (warp_on) { segtype = segment_class(p, yl, xv_raw >> 5); warp_on = segtype != SEG_GENERAL; }
     float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-    __shared__ __align__(16) float trail_smem[TrailSmem<ODD ? -1 : COLL>::floats];
-    __shared__ __align__(8) unsigned long long trail_bar[BX / 32];
-    float* tbuf = trail_smem + (trail ? (threadIdx.x >> 5) * Q * TRAIL_W : 0);
-    unsigned long long* tbar = trail_bar + (threadIdx.x >> 5);
-    TrailCtx tc; tc.on = false;
     if (warp_on) {
         const int x0 = xv << 2;
         // cells of this thread the general kernel owns (even phase only: the host never hands SEG_MIXED segments to the odd branch of
@@ -515,7 +380,6 @@ __global__ void __launch_bounds__(BX, vec_min_blocks(COLL, ODD)) step_vec_kernel
                 float4 v = ld4(p.A[q] + r0 + x0);
                 g[0][q].a = make_float2(v.x, v.y); g[1][q].a = make_float2(v.z, v.w);
             }
-            if (trail) tc = trail_begin<true>(p, yl, xv_raw >> 5, lane, tbuf, tbar);       // behind the loads: its L2 round trips hide in their latency
         } else {
             // g_q(x) = A[opp q][x - c_q]: source row y - c_y, source column x - c_x.  All vector loads first, then the
             // (predicated) scalar loads of the first / last lane, then the shuffles -- nothing between the loads that
@@ -570,7 +434,7 @@ __global__ void __launch_bounds__(BX, vec_min_blocks(COLL, ODD)) step_vec_kernel
                 collide_cm_v<true>(rx, g[hf], ux, uy, forced, Fx, Fy, optimal_rate_v(m.rho, jm, pm, av));
             }
         }
-        if (COLL == C_CMOPT && act && !trail) { s0 = hsum(acc0); s1 = hsum(acc1); s2 = hsum(acc2); }
+        if (COLL == C_CMOPT && act) { s0 = hsum(acc0); s1 = hsum(acc1); s2 = hsum(acc2); }
         if (p.rho_out && act) {
             const long long ln = (long long)yl * p.nx + x0;
             st4_masked(p.rho_out + ln, rho4[0].x, rho4[0].y, rho4[1].x, rho4[1].y, skip);
@@ -596,11 +460,6 @@ __global__ void __launch_bounds__(BX, vec_min_blocks(COLL, ODD)) step_vec_kernel
             }
         }
     }
-    if (trail) {                                                             // this is an even step: t + 1 is odd
-        if (!warp_on) tc = trail_begin<true>(p, yl, xv_raw >> 5, lane, tbuf, tbar);
-        trail_end<true>(p, tc, xv_raw >> 5, lane, tbuf, tbar, s0, s1, s2);
-        trail_row_done(p, yl, lane);
-    }
     if (COLL == C_CMOPT && p.partials) warp_partials(s0, s1, s2, p.partials + 3 * VEC_PARTS * ((long long)blockIdx.y * gridDim.x + blockIdx.x));
 }
 
@@ -625,16 +484,10 @@ __global__ void __launch_bounds__(BX, COLL == 3 ? LBM_ODD_MIN_BLOCKS_OPT : LBM_O
     const int lane = threadIdx.x & 31;
     const int sx = blockIdx.x * (BX / 32) + (threadIdx.x >> 5);       // segment of this warp within the row
     const int yl = blockIdx.y;
-    const bool trail = COLL == C_CMOPT && p.trail > 0;                // block rows beyond the slab only sum trailing moments
-    bool warp_on = sx < p.nsx && yl < p.nyl;
+    bool warp_on = sx < p.nsx;
     uint8_t segtype = SEG_VEC;
-    if (warp_on && p.segmask) { segtype = p.segmask[(long long)yl * p.nsx + sx]; warp_on = segtype != SEG_GENERAL; }
+    if (warp_on) { segtype = segment_class(p, yl, sx); warp_on = segtype != SEG_GENERAL; }
     float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-    __shared__ __align__(16) float trail_smem[TrailSmem<COLL>::floats];
-    __shared__ __align__(8) unsigned long long trail_bar[BX / 32];
-    float* tbuf = trail_smem + (trail ? (threadIdx.x >> 5) * Q * TRAIL_W : 0);
-    unsigned long long* tbar = trail_bar + (threadIdx.x >> 5);
-    TrailCtx tc; tc.on = false;
     if (warp_on) {
         float avg_raw[3] = {1.f, 1.f, 1.f};
         if (COLL == C_CMOPT) { avg_raw[0] = __ldg(p.avg); avg_raw[1] = __ldg(p.avg + 1); avg_raw[2] = __ldg(p.avg + 2); }
@@ -672,7 +525,6 @@ __global__ void __launch_bounds__(BX, COLL == 3 ? LBM_ODD_MIN_BLOCKS_OPT : LBM_O
             else if (cx(q) < 0) { g[0][q].a.x = r[x + 1]; g[0][q].a.y = r[x + 33]; g[1][q].a.x = r[x + 65]; g[1][q].a.y = r[xw_hi]; }
             else { g[0][q].a.x = r[x]; g[0][q].a.y = r[x + 32]; g[1][q].a.x = r[x + 64]; g[1][q].a.y = r[x + 96]; }
         }
-        if (trail) tc = trail_begin<false>(p, yl, sx, lane, tbuf, tbar);               // behind the loads: its L2 round trips hide in their latency
         float2 rho4[2], ux4[2], uy4[2];
         AdapterAvg av{};
         if (COLL == C_CMOPT) { av.inv_rho = fast_rcp(avg_raw[0]); av.inv_j = fast_rcp(avg_raw[1]); av.inv_pi = fast_rcp(avg_raw[2]); }
@@ -696,7 +548,7 @@ __global__ void __launch_bounds__(BX, COLL == 3 ? LBM_ODD_MIN_BLOCKS_OPT : LBM_O
                 collide_cm_v<true>(rx, g[hf], ux, uy, forced, Fx, Fy, optimal_rate_v(m.rho, jm, pm, av));
             }
         }
-        if (COLL == C_CMOPT && !trail) { s0 = hsum(acc0); s1 = hsum(acc1); s2 = hsum(acc2); }
+        if (COLL == C_CMOPT) { s0 = hsum(acc0); s1 = hsum(acc1); s2 = hsum(acc2); }
         const bool k0 = !(skip & 1u), k1 = !(skip & 2u), k2 = !(skip & 4u), k3 = !(skip & 8u);
         if (p.rho_out) {
             const long long ln = (long long)yl * p.nx + x;
@@ -723,11 +575,6 @@ __global__ void __launch_bounds__(BX, COLL == 3 ? LBM_ODD_MIN_BLOCKS_OPT : LBM_O
             if (k2) r[x + 64 + cx(q)] = g[1][q].a.x;
             if (k3) r[d3] = g[1][q].a.y;
         }
-    }
-    if (trail) {                                                             // this is an odd step: t + 1 is even
-        if (!warp_on) tc = trail_begin<false>(p, yl, sx, lane, tbuf, tbar);
-        trail_end<false>(p, tc, sx, lane, tbuf, tbar, s0, s1, s2);
-        trail_row_done(p, yl, lane);
     }
     if (COLL == C_CMOPT && p.partials) warp_partials(s0, s1, s2, p.partials + 3 * VEC_PARTS * ((long long)blockIdx.y * gridDim.x + blockIdx.x));
 }
@@ -906,23 +753,6 @@ struct mixed_general_cell {
     __device__ bool operator()(long long ln) const {
         const int yl = (int)(ln / p.nx), x = (int)(ln - (long long)yl * p.nx);
         return mask[(long long)yl * p.nsx + x / SEG] == SEG_MIXED && cell_is_general(p, x, yl);
-    }
-};
-
-// trailing moments: class of every segment (one block per segment) and the cells the step kernels leave to the list pass
-__global__ void __launch_bounds__(SEG) build_mclass_kernel(const Params p, uint8_t* mclass) {
-    const int yl = blockIdx.y, sx = blockIdx.x, x = sx * SEG + (int)threadIdx.x;
-    const bool in = x < p.nx;
-    const bool ex = in && trail_excluded(p, x, yl);
-    const int nex = __syncthreads_count(ex), nin = __syncthreads_count(in);
-    if (threadIdx.x == 0) mclass[(long long)yl * p.nsx + sx] = nex == 0 ? 0 : (nex == nin ? 2 : 1);
-}
-struct trail_list_cell {
-    Params p; const uint8_t* mclass;
-    __device__ bool operator()(long long ln) const {
-        const int yl = (int)(ln / p.nx), x = (int)(ln - (long long)yl * p.nx);
-        const uint8_t c = mclass[(long long)yl * p.nsx + x / SEG];
-        return c == 2 || (c == 1 && trail_excluded(p, x, yl));
     }
 };
 

@@ -328,13 +328,14 @@ def test_graph_replay_is_bit_identical_to_stream_launches(name, adapter_mode, mo
             assert l_graph == l_plain           # the launch counter counts the kernels inside the replayed graphs
 
 
-# ---------------------------------------------------------------- lbm_run_from_host: the time-skewed band pipeline
+# ---------------------------------------------------------------- lbm_run_from_host: the skewed band pipeline
 @pytest.mark.parametrize("nx,ny,coll,nsteps", [(128, 200, cases.BGK, 1), (128, 200, cases.BGK, 2), (128, 200, cases.MRT, 5), (128, 200, cases.CM, 7),
                                                (128, 200, cases.BGK, 30), (256, 1024, cases.BGK, 9), (64, 1000, cases.MRT, 40), (132, 64, cases.CM, 3)])
 def test_run_from_host_equals_the_three_calls(nx, ny, coll, nsteps):
-    """init from host fields + n steps + macroscopics to host in one call: row bands stepped in a time-skewed order while the other
-    bands are still being copied.  Same bits as lbm_init_fields + lbm_step_with_macroscopics + lbm_get_macroscopics, whether the
-    dependency wedges at the periodic seam stay apart (n small against the band count) or meet (n = 30 on 13 bands)."""
+    """init from host fields + n steps + macroscopics to host in one call: row bands stepped in a skewed order (band j covers the rows
+    [r0 - t, r1 - t) at step t, so it runs all its steps as soon as it has arrived) while the other bands are still being copied, the
+    wedge at the periodic seam level by level at the end.  Same bits as lbm_init_fields + lbm_step_with_macroscopics +
+    lbm_get_macroscopics, with one band or many, n from 1 to 40."""
     case = _tg_case(nx, ny, coll)
     case.u_max = np.float32(0.04)
     rho0, u0 = case.init_fields()
@@ -514,34 +515,13 @@ def test_lagged_adapter_with_mixed_segments():
     assert np.isfinite(f_t).all() and np.abs(f_t - f_s).max() <= 1e-6, float(np.abs(f_t - f_s).max())
 
 
-TRAIL_CASES = [("tg", 512, 40, (True, True)), ("tg", 128, 300, (True, True)), ("lid", 384, 40, (False, False)), ("cyl_ibm", 512, 48, (False, False)),
-               ("pois", 256, 24, (True, False)), ("cyl_flag", 256, 64, (False, False))]
-
-
-@pytest.mark.parametrize("kind,nx,ny,periodic", TRAIL_CASES)
-@pytest.mark.parametrize("rows", [0, 2, 5])
-def test_trailing_moments_equal_the_moments_prepass(kind, nx, ny, periodic, rows):
-    """CM<2,OptimalAdapter>, LBM_ADAPTER_EXACT: the grid sums of step t + 1 taken by the step kernels of step t out of L2, `rows` rows
-    behind the rows they collide (0 = the engine's choice), plus the list pass for general cells and their neighbours, against the
-    moments pre-pass (LBM_B200_TRAIL=0).  Same sums up to fp32 / fp64 summation order: fields agree to 1e-6 after 28 steps (as in the lagged-adapter test); both stay within the usual
-    bounds of the CPU oracle.  Steps are cut into calls so that plain launches, the step that leads into the steady state and CUDA-graph
-    replays (16 steps each) all occur, with periodic wrap, walls (neighbour-reading corner BCs), flag bodies, IBM bodies and a force."""
-    nu = 1.0 / 6.0 if kind in ("tg", "pois") else (0.03 if kind == "lid" else float(cases._cyl_nu(ny)))
-    um = {"tg": 0.04, "pois": 0.05, "lid": 0.1}.get(kind, 0.05)
-    force = cases._pois_force(ny) if kind == "pois" else (0.0, 0.0)
-    case = cases.Case(f"trail_{kind}_{nx}x{ny}", nx, ny, cases.CM_OPT, nu, periodic, um, kind, force=force, np_markers=24, scale=nx // 128)
-    chunks = [3, 20, 1, 4]
-    n = sum(chunks)
-    env_t = {"LBM_B200_TRAIL": "1", "LBM_B200_GRAPH": "1"}
-    if rows:
-        env_t["LBM_B200_TRAIL_ROWS"] = str(rows)
-    (rho_t, u_t), f_t, info_t = _steps_fields(case, n, env=env_t, chunks=chunks)
-    (rho_s, u_s), f_s, info_s = _steps_fields(case, n, env={"LBM_B200_TRAIL": "0", "LBM_B200_GRAPH": "1"}, chunks=chunks)
-    assert np.isfinite(f_t).all()
-    assert info_t.kernel_launches < info_s.kernel_launches          # no moments_vec_kernel in the steady state
-    assert np.abs(f_t - f_s).max() <= 1e-6 and np.abs(rho_t - rho_s).max() <= 2e-6 and np.abs(u_t - u_s).max() <= 1e-6, float(np.abs(f_t - f_s).max())
-    o = make_oracle(case)
-    o.init(*case.init_fields())
-    o.step(n)
-    assert np.abs(f_t - o.populations()).max() <= TOL_F * n ** 0.5
-    assert np.abs(rho_t - o.macroscopics()[0]).max() <= TOL_RHO * n ** 0.5
+@pytest.mark.parametrize("kind,nx,ny,coll", [("lid", 512, 48, cases.CM_OPT), ("cyl_ibm", 640, 64, cases.MRT), ("cyl_flag", 384, 64, cases.BGK)])
+def test_all_vector_rectangle_changes_nothing(kind, nx, ny, coll):
+    """Warps inside the largest rectangle of all-vector segments (found on the host) skip the per-segment class lookup — with walls all
+    round, with a body in the middle (the rectangle lies beside it).  LBM_B200_PURE_RECT=0 makes every warp look its class up: same bits."""
+    nu = 0.03 if kind == "lid" else float(cases._cyl_nu(ny))
+    case = cases.Case(f"rect_{kind}_{nx}x{ny}", nx, ny, coll, nu, (False, False), 0.1 if kind == "lid" else 0.05, kind, np_markers=24, scale=nx // 128)
+    (rho_a, u_a), f_a, _ = _steps_fields(case, 9)
+    (rho_b, u_b), f_b, _ = _steps_fields(case, 9, env={"LBM_B200_PURE_RECT": "0"})
+    assert np.isfinite(f_a).all()
+    assert np.array_equal(f_a, f_b) and np.array_equal(rho_a, rho_b) and np.array_equal(u_a, u_b)
