@@ -46,6 +46,7 @@ NX = NY = 32768
 NU = 1.0 / 6.0
 U0 = 0.04 / 256.0          # TaylorGreenInit: u_max / SCALE, SCALE = NX/128 (taylorGreenFunctors.cuh:11-13, defines.hpp:20-23)
 BYTES_PER_UPDATE = 72.0
+NCU_TRAFFIC_PER_LAUNCH = 77.260e9       # dram bytes per launch of the 32768^2 BGK step kernels, ncu --set full (profiles/r02_ncu_bench_kernel.md)
 EX = os.path.join(ROOT, "examples", "_bin")
 REF = os.path.join(ROOT, "oracle", "_ref", "bin")
 
@@ -311,8 +312,8 @@ def main():
     achieved = BYTES_PER_UPDATE * nloc / (kern_ms * 1e-3) / 1e9
     peak, peak_src = measured_peak()
     # dram__bytes_read.sum + dram__bytes_write.sum per launch: a CITATION of the ncu --set full capture of this command at N = 1
-    # (profiles/r01_ncu_bench_kernel.md: 77.261 GB odd phase, 77.259 GB even phase), scaled by the rows this rank owns; not re-measured per run
-    traffic = 77.260e9 * (nloc / float(NX * NY)) if (nx == NX and args.collision == "BGK") else None
+    # (profiles/r02_ncu_bench_kernel.md, mean of the odd- and even-phase kernels), scaled by the rows this rank owns; not re-measured per run
+    traffic = NCU_TRAFFIC_PER_LAUNCH * (nloc / float(NX * NY)) if (nx == NX and args.collision == "BGK") else None
 
     # ---------------- correctness of the state the timed region left behind (outside the timed region) ----------------
     # one more step that also stores rho / u, then the reference's Taylor-Green metric with both sums taken on the device
@@ -333,9 +334,12 @@ def main():
     if not args.no_e2e:
         from cuda_lbm_b200._capi import lib, check as chk
         import ctypes as C
-        h_rho, h_u = C.c_void_p(), C.c_void_p()
+        # pinned host buffers on the NUMA node of this rank's GPU (lbm_host_alloc), separate ones for the input and the result
+        h_rho, h_u, o_rho, o_u = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
         chk(lib().lbm_host_alloc(C.byref(h_rho), nloc * 4))
         chk(lib().lbm_host_alloc(C.byref(h_u), nloc * 8))
+        chk(lib().lbm_host_alloc(C.byref(o_rho), nloc * 4))
+        chk(lib().lbm_host_alloc(C.byref(o_u), nloc * 8))
         # host-resident input: the Init functor's rho,u for this slab, produced once outside the timed region
         chk(lib().lbm_reserve_macroscopics(eng._h))
         eng.init_taylor_green(NU, u0)
@@ -347,7 +351,7 @@ def main():
         # (lbm_run_from_host; peer-mapped slabs synchronise their faces level by level on the device)
         api, failed = None, 0.0
         try:
-            solver.run_from_host(h_rho.value, h_u.value, args.steps, h_rho.value, h_u.value)
+            solver.run_from_host(h_rho.value, h_u.value, args.steps, o_rho.value, o_u.value)
             api = ("lbm_run_from_host (copies and kernels pipelined over row bands)" if solver.mode in ("single", "direct")
                    else "lbm_init_fields_local + lbm_step_with_macroscopics + lbm_get_macroscopics")
         except L.LbmError as ex:        # never lose the bench line over the e2e leg: every rank falls back together
@@ -361,19 +365,19 @@ def main():
             chk(lib().lbm_init_fields_local(eng._h, h_rho, h_u))
             solver.barrier_after_init()
             solver.step(args.steps, macroscopics=True)
-            eng.macroscopics_into(h_rho.value, h_u.value)
+            eng.macroscopics_into(o_rho.value, o_u.value)
             api = "lbm_init_fields_local + lbm_step_with_macroscopics + lbm_get_macroscopics (" + (api or "another rank's lbm_run_from_host failed") + ")"
         barrier()
         dt = max_over_ranks(time.perf_counter() - t0)
         # the result in the HOST buffers is what the user gets: check it too (mean of rho over this rank's rows, summed over ranks)
-        h_sum = float(np.ctypeslib.as_array(C.cast(h_rho, C.POINTER(C.c_float)), shape=(nloc,)).sum(dtype=np.float64))
+        h_sum = float(np.ctypeslib.as_array(C.cast(o_rho, C.POINTER(C.c_float)), shape=(nloc,)).sum(dtype=np.float64))
         h_mean = sum_over_ranks([h_sum])[0] / (float(nx) * ny)
         e2e = {"value": nx * ny * args.steps / dt / 1e6, "unit": "MLUPS",
                "h2d_bytes_per_step": 12.0 * nloc / args.steps, "d2h_bytes_per_step": 12.0 * nloc / args.steps,
-               "segment": f"pinned host rho,u -> H2D -> {args.steps} steps -> D2H rho,u ({12 * nloc / 1e9:.2f} GB each way per rank; output written over the input buffers)", "api": api,
+               "segment": f"pinned host rho,u -> H2D -> {args.steps} steps -> D2H rho,u ({12 * nloc / 1e9:.2f} GB each way per rank; separate input and output buffers, allocated on the GPU's NUMA node)", "api": api,
                "seconds": dt, "host_result_mean_rho": h_mean}
-        lib().lbm_host_free(h_rho)
-        lib().lbm_host_free(h_u)
+        for b in (h_rho, h_u, o_rho, o_u):
+            lib().lbm_host_free(b)
     eng.close()
 
     cpu = None
@@ -403,8 +407,8 @@ def main():
                 "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "check": check,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": traffic,
-                             "traffic_source": "citation: ncu --set full of this command at N = 1, dram__bytes_read.sum + dram__bytes_write.sum per launch, mean of the odd / even phase captures (profiles/r01_ncu_bench_kernel.md), scaled by rows per rank; not re-measured by this run",
-                             "peak_source": peak_src, "kernel": "lbm::step_vec_kernel<BGK, odd|even> (fused pull + collide + push, 4 cells/thread)",
+                             "traffic_source": "citation: ncu --set full of this command at N = 1, dram__bytes_read.sum + dram__bytes_write.sum per launch, mean of the odd / even phase captures (profiles/r02_ncu_bench_kernel.md), scaled by rows per rank; not re-measured by this run",
+                             "peak_source": peak_src, "kernel": "lbm::step_odd_kernel<BGK> (odd AA phase) / lbm::step_vec_kernel<BGK, even> — fused pull + collide + push, 4 cells per thread, one launch per step",
                              "algorithmic_bytes_per_launch": BYTES_PER_UPDATE * nloc, "kernel_ms": kern_ms},
                 "cpu_baseline": cpu, "reference_cuda": ref_cuda, "configs": configs}
         print(json.dumps(line), flush=True)

@@ -26,6 +26,7 @@ enum : int {
     REGULARIZED_BOUNCE_BACK_CORNER = 12
 };
 constexpr uint8_t FLAG_IBM = 0x80;   // node lies in a marker stencil: force comes from ibm_force[]
+constexpr uint8_t FLAG_OWNED = 0x40; // FLUID node handed to the general kernel: a boundary node reads its post-stream populations (nbr_gather)
 constexpr uint8_t FLAG_MASK = 0x1f;
 
 struct Params {
