@@ -62,7 +62,6 @@ struct Params {
     // live one L2 round trip longer (the cavity's vector kernels ran at 219 / 249 us against 197 / 213 us for the same operator on
     // the periodic box), and ptxas moves the test in front of the loads however the source orders them.
     int pure_y0, pure_y1, pure_s0, pure_s1;
-    int pdl;                // launched as a programmatic dependent of the reduction: read the grid means behind griddepcontrol.wait
     const long long* gen_cells; long long gen_cell_count;
     // direct y-slab coupling over NVLink peer memory: [0] = the lower neighbour's top edge row, [1] = the upper neighbour's
     // bottom edge row, addressed as peer[s] + plane * peer_plane[s] + peer_off[s] + x.  nullptr = use this slab's ghost rows.

@@ -177,13 +177,6 @@ constexpr int vec_min_blocks(int coll, bool odd) {
 #ifndef LBM_AVG_EARLY
 #define LBM_AVG_EARLY 1
 #endif
-// Programmatic dependent launch (engine_step.inc launch_vec / launch_odd): the CM<2,OptimalAdapter> step kernel is allowed to START while
-// the reduction that produces the grid means is still running — its population loads depend on the previous STEP only, which is complete
-// before the reduction starts.  The means are read behind this wait (no-op in an ordinary launch), and past L1.
-__device__ __forceinline__ void wait_for_grid_means(const float* avg, float out[3]) {
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    out[0] = __ldcg(avg); out[1] = __ldcg(avg + 1); out[2] = __ldcg(avg + 2);
-}
 #ifndef LBM_ST_HINT
 #define LBM_ST_HINT 0
 #endif
@@ -360,7 +353,7 @@ __global__ void __launch_bounds__(BX, vec_min_blocks(COLL, ODD)) step_vec_kernel
         // would cost a second full memory latency per thread.
         float avg_raw[3] = {1.f, 1.f, 1.f};
 #if LBM_AVG_EARLY
-        if (COLL == C_CMOPT && !p.pdl) { avg_raw[0] = __ldg(p.avg); avg_raw[1] = __ldg(p.avg + 1); avg_raw[2] = __ldg(p.avg + 2); }
+        if (COLL == C_CMOPT) { avg_raw[0] = __ldg(p.avg); avg_raw[1] = __ldg(p.avg + 1); avg_raw[2] = __ldg(p.avg + 2); }
 #endif
         V2 g[2][Q];                                   // g[h][q]: cells x0+2h, x0+2h+1 side by side (packed fp32 lanes)
         // neighbours inside the warp exchange the boundary element; a row starts at lane 0 (blockDim.x % 32 == 0)
@@ -416,7 +409,6 @@ __global__ void __launch_bounds__(BX, vec_min_blocks(COLL, ODD)) step_vec_kernel
         float2 rho4[2], ux4[2], uy4[2];
         AdapterAvg av{};
 #if LBM_AVG_EARLY
-        if (COLL == C_CMOPT && p.pdl) wait_for_grid_means(p.avg, avg_raw);          // the populations are in flight
         if (COLL == C_CMOPT) { av.inv_rho = fast_rcp(avg_raw[0]); av.inv_j = fast_rcp(avg_raw[1]); av.inv_pi = fast_rcp(avg_raw[2]); }
 #else
         if (COLL == C_CMOPT) av = load_adapter_avg(p.avg);
@@ -498,7 +490,7 @@ __global__ void __launch_bounds__(BX, COLL == 3 ? LBM_ODD_MIN_BLOCKS_OPT : LBM_O
     float s0 = 0.f, s1 = 0.f, s2 = 0.f;
     if (warp_on) {
         float avg_raw[3] = {1.f, 1.f, 1.f};
-        if (COLL == C_CMOPT && !p.pdl) { avg_raw[0] = __ldg(p.avg); avg_raw[1] = __ldg(p.avg + 1); avg_raw[2] = __ldg(p.avg + 2); }
+        if (COLL == C_CMOPT) { avg_raw[0] = __ldg(p.avg); avg_raw[1] = __ldg(p.avg + 1); avg_raw[2] = __ldg(p.avg + 2); }
         const int x = sx * SEG + lane;                                // cells x, x + 32, x + 64, x + 96
         const long long r0 = rowoff(p, yl);
         const int gen = p.t & 1;
@@ -535,7 +527,6 @@ __global__ void __launch_bounds__(BX, COLL == 3 ? LBM_ODD_MIN_BLOCKS_OPT : LBM_O
         }
         float2 rho4[2], ux4[2], uy4[2];
         AdapterAvg av{};
-        if (COLL == C_CMOPT && p.pdl) wait_for_grid_means(p.avg, avg_raw);          // the populations are in flight
         if (COLL == C_CMOPT) { av.inv_rho = fast_rcp(avg_raw[0]); av.inv_j = fast_rcp(avg_raw[1]); av.inv_pi = fast_rcp(avg_raw[2]); }
         const Relax rx = relax_of(p);
         const bool forced = p.fx != 0.0f || p.fy != 0.0f;
@@ -664,7 +655,6 @@ __global__ void __launch_bounds__(256) reduce_kernel(const float* partials, long
                                                      double inv_n, int write_avg, const SlabNet* net, unsigned long long tag) {
     __shared__ bool last;
     double o[3];
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");     // a step kernel launched as a programmatic dependent may start its loads now
     block_sum3(partials, nparts, (long long)blockIdx.x * 256 + threadIdx.x, (long long)gridDim.x * 256, o);
     if (threadIdx.x < 3) stage[3 * blockIdx.x + threadIdx.x] = o[threadIdx.x];
     __threadfence();
