@@ -169,8 +169,9 @@ int lbm_step_with_macroscopics(lbm_handle* h, int32_t nsteps);
 /* One driver segment of the reference in one call (src/main.cu:77-147: init<Scenario>(), n iterations of the time loop,
  * update_macroscopics()): populations from rho / u in host memory (this slab's rows, as lbm_init_fields_local), nsteps time
  * steps, rho / u of the last step back into host memory (as lbm_get_macroscopics).  Same results, bit for bit, as those three
- * calls.  When the slab is the whole periodic domain on the vectorised path, the slab is stepped in row bands in a time-skewed
- * order so that the host->device copy, the kernels and the device->host copy of different bands overlap (pinned host memory,
+ * calls.  When the slab is the whole periodic domain on the vectorised path, the slab is stepped in row bands in a skewed order
+ * (band j covers the rows [r0 - t, r1 - t) at step t and runs all its steps as soon as it has arrived; needs ny_local >= 4 nsteps + 16,
+ * otherwise the three calls run) so that the host->device copy, the kernels and the device->host copy of different bands overlap (pinned host memory,
  * lbm_host_alloc, for full effect).  The output arrays may be the input arrays.  Blocks until the output is complete.
  * Several slabs: supported with peer-mapped neighbours on both faces; every slab makes the call (one thread or process each), after
  * all of them have finished their previous work (lbm_sync + barrier, as for lbm_init_*); the slab faces are synchronised level by
@@ -293,7 +294,9 @@ int lbm_peer_detach(lbm_handle* h);
  * can then no longer enqueue.  Leave it off (default) when one thread enqueues the slabs one after the other. */
 int lbm_set_lookahead(lbm_handle* h, int32_t bounded);
 
-/* Pinned host memory helpers for callers that want full-speed host<->device copies. */
+/* Pinned host memory helpers for callers that want full-speed host<->device copies.  lbm_host_alloc places the pages on the NUMA node
+ * of the CURRENT device (cudaSetDevice first) where the box reports one (sysfs numa_node), so that a slab's copies do not cross the
+ * socket interconnect; LBM_B200_HOST_NUMA=0 leaves the placement to the caller's own CPU affinity. */
 int lbm_host_alloc(void** out, int64_t bytes);
 int lbm_host_free(void* p);
 
