@@ -54,7 +54,7 @@ struct lbm_handle {
     cudaStream_t side_stream = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr; bool overlap = true;
     // small grids are bound by the host's launch rate, not by the GPU: lbm_step(h, n) replays a captured CUDA graph of
     // 2*GRAPH_PAIRS steps (an odd/even pair repeats identically: only the parity of t reaches the kernels)
-    struct StepGraph { cudaGraphExec_t exec = nullptr; std::string key; long long launches = 0; int d_avg = 0, d_pre = 0, d_nbrg = 0; } graph[2][2];   // [parity][16 / 128 steps]
+    struct StepGraph { cudaGraphExec_t exec = nullptr; std::string key; long long launches = 0; int d_avg = 0, d_pre = 0, d_nbrg = 0; } graph[2];
     int graph_mode = -1;            // LBM_B200_GRAPH: 0 never, 1 whenever possible, unset = slabs of up to 2^22 cells
     cudaEvent_t ev_bridge[2] = {nullptr, nullptr};
     // lbm_set_lookahead: lbm_step(h, n) on a peer-mapped slab keeps at most 3 x 8 steps enqueued ahead of the device (events recorded
@@ -224,7 +224,7 @@ extern "C" int lbm_destroy(lbm_handle* h) {
                     h->partials, h->stage, h->sums, h->avg, h->rho_out, h->u_out, h->mass_acc, h->segmask, h->gen_list, h->gen_cells, h->val_stage};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
-    for (auto& gp : h->graph) for (auto& g : gp) if (g.exec) cudaGraphExecDestroy(g.exec);
+    for (auto& g : h->graph) if (g.exec) cudaGraphExecDestroy(g.exec);
     for (auto& e : h->ev_bridge) if (e) cudaEventDestroy(e);
     for (auto& e : h->ev_throttle) if (e) cudaEventDestroy(e);
     for (auto& e : h->ev_band) cudaEventDestroy(e);
