@@ -29,6 +29,8 @@ constexpr uint8_t FLAG_IBM = 0x80;   // node lies in a marker stencil: force com
 constexpr uint8_t FLAG_OWNED = 0x40; // FLUID node handed to the general kernel: a boundary node reads its post-stream populations (nbr_gather)
 constexpr uint8_t FLAG_MASK = 0x1f;
 
+constexpr int COLCLASS_MAX = 256;     // segment columns covered by Params::colclass (nx <= 32768)
+
 struct Params {
     float* A[Q];            // slot planes, each (ny_local+2) rows of nx floats; row 0 / ny_local+1 are ghost rows
     float* A0[2];           // rest-population plane used at odd / even timesteps (same pointer unless QK_D1)
@@ -62,6 +64,9 @@ struct Params {
     // live one L2 round trip longer (the cavity's vector kernels ran at 219 / 249 us against 197 / 213 us for the same operator on
     // the periodic box), and ptxas moves the test in front of the loads however the source orders them.
     int pure_y0, pure_y1, pure_s0, pure_s1;
+    // and for the rows of that rectangle, the class of every segment COLUMN whose class does not change over those rows (255: it does,
+    // look it up) — the cavity's two wall columns are mixed segments in every interior row, and a block is held by its slowest warp
+    uint8_t colclass[COLCLASS_MAX];
     const long long* gen_cells; long long gen_cell_count;
     // direct y-slab coupling over NVLink peer memory: [0] = the lower neighbour's top edge row, [1] = the upper neighbour's
     // bottom edge row, addressed as peer[s] + plane * peer_plane[s] + peer_off[s] + x.  nullptr = use this slab's ghost rows.
@@ -69,6 +74,7 @@ struct Params {
     long long plane;        // floats per slot plane of this slab: A[q] == A[0] + q * plane
 };
 constexpr int SEG = 128;
+constexpr uint8_t SEG_LOOKUP = 255;
 
 __device__ __forceinline__ long long rowoff(const Params& p, int yl) { return (long long)(yl + 1) * p.nx; }
 // start of row yl of a slot plane; rows -1 and nyl resolve to the neighbour slab's edge row when it is peer-mapped

@@ -95,6 +95,7 @@ struct lbm_handle {
     // general-path segments (kernels.cuh): mask per 128-cell segment + compact list, rebuilt lazily
     uint8_t* segmask = nullptr; int* gen_list = nullptr; int gen_count = 0; int nsx = 0; bool segs_dirty = true;
     long long* gen_cells = nullptr; long long gen_cell_count = 0, gen_cell_cap = 0;      // general cells of the mixed segments (local node ids)
+    uint8_t colclass[COLCLASS_MAX] = {};      // Params::colclass, valid for the rows pure[0] .. pure[1]
     int pure[4] = {0, 0, 0, 0};     // rows [0],[1]) x segments [2],[3]): the largest rectangle of all-vector segments (Params::pure_*)
     // adapter
     float* partials = nullptr; long long n_partials = 0; double* stage = nullptr; double* sums = nullptr; float* avg = nullptr; int avg_for_ts = -1; int pre_for_ts = -1;
@@ -163,6 +164,7 @@ static Params make_params(lbm_handle* h, int t) {
     p.ibm_nodes = h->ibm_nodes; p.ibm_force = h->ibm_force; p.ibm_count = h->ibm_count;
     p.avg = h->avg; p.partials = nullptr; p.rho_out = nullptr; p.u_out = nullptr;
     p.pure_y0 = h->pure[0]; p.pure_y1 = h->pure[1]; p.pure_s0 = h->pure[2]; p.pure_s1 = h->pure[3];
+    memcpy(p.colclass, h->colclass, sizeof(p.colclass));
     p.segmask = nullptr; p.nsx = h->nsx; p.gen_list = nullptr; p.gen_cells = nullptr; p.gen_cell_count = 0; p.plane = (long long)h->plane;
     for (int sd = 0; sd < 2; sd++) { p.peer[sd] = h->peer[sd].attached ? h->peer[sd].base : nullptr; p.peer_plane[sd] = h->peer[sd].plane; p.peer_off[sd] = h->peer[sd].off; }
     return p;

@@ -201,7 +201,11 @@ __device__ __forceinline__ void st4(float* p, float a, float b, float c, float d
 
 // class of segment sx of row yl; no memory access inside the all-vector rectangle
 __device__ __forceinline__ uint8_t segment_class(const Params& p, int yl, int sx) {
-    if (!p.segmask || (yl >= p.pure_y0 && yl < p.pure_y1 && sx >= p.pure_s0 && sx < p.pure_s1)) return SEG_VEC;
+    if (!p.segmask) return SEG_VEC;
+    if (yl >= p.pure_y0 && yl < p.pure_y1) {
+        if (sx >= p.pure_s0 && sx < p.pure_s1) return SEG_VEC;
+        if (sx < COLCLASS_MAX) { const uint8_t c = p.colclass[sx]; if (c != SEG_LOOKUP) return c; }     // kernel parameter space: no memory round trip
+    }
     return p.segmask[(long long)yl * p.nsx + sx];
 }
 
