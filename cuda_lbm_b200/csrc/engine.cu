@@ -57,8 +57,8 @@ struct lbm_handle {
     struct StepGraph { cudaGraphExec_t exec = nullptr; std::string key; long long launches = 0; int d_avg = 0, d_pre = 0, d_nbrg = 0; } graph[2];
     int graph_mode = -1;            // LBM_B200_GRAPH: 0 never, 1 whenever possible, unset = slabs of up to 2^22 cells
     cudaEvent_t ev_bridge[2] = {nullptr, nullptr};
-    // lbm_set_lookahead: lbm_step(h, n) on a peer-mapped slab keeps at most 3 x 8 steps enqueued ahead of the device (events recorded
-    // every 8 steps, the host waits for the one of 24 steps ago).  For callers that drive every slab from its own thread: when several
+    // lbm_set_lookahead: lbm_step(h, n) on a peer-mapped slab keeps at most 3 x 4 steps enqueued ahead of the device (events recorded
+    // every 4 steps, the host waits for the one of 12 steps ago).  For callers that drive every slab from its own thread: when several
     // slabs share ONE device (more slabs than GPUs) their blocked launches otherwise exhaust the context's launch queue while the slab
     // they wait for cannot enqueue any more (seen with 4 slabs x 60 steps on one B200).  Off by default: a caller that enqueues the
     // slabs one after the other from a single thread needs the unbounded queue.

@@ -288,7 +288,7 @@ int lbm_peer_attach(lbm_handle* h, int side, const void* desc);
  * span any number of slabs. */
 int lbm_peer_attach_all(lbm_handle* h, const void* descs, int32_t count);
 int lbm_peer_detach(lbm_handle* h);
-/* bounded != 0: lbm_step(h, n) on a peer-mapped slab keeps at most 24 steps enqueued ahead of the device (the host waits inside the
+/* bounded != 0: lbm_step(h, n) on a peer-mapped slab keeps at most 12 steps enqueued ahead of the device (the host waits inside the
  * call).  For callers that drive every slab from its own host thread and may run more slabs than GPUs (the header shim with
  * LBM_B200_GPUS): slabs that share a device would otherwise fill the context's launch queue with launches that wait for a slab which
  * can then no longer enqueue.  Leave it off (default) when one thread enqueues the slabs one after the other. */

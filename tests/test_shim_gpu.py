@@ -213,7 +213,14 @@ def test_call_orders_and_per_step_forces(tmp_path):
 
 def _run_slabs_env(name, cwd, gpus, *args):
     env = dict(os.environ, LBM_B200_GPUS=str(gpus))
-    r = subprocess.run([need(os.path.join(EX, name))] + [str(a) for a in args], cwd=cwd, env=env, capture_output=True, text=True, timeout=900)
+    cmd = [need(os.path.join(EX, name))] + [str(a) for a in args]
+    r = subprocess.run(cmd, cwd=cwd, env=env, capture_output=True, text=True, timeout=900)
+    if r.returncode != 0 and gpus > 1 and "handshake timed out" in r.stdout + r.stderr:
+        # Several slabs that SHARE one device (this box; a test topology — in production every slab has its own GPU) spin for one another
+        # on that device, and about one such run in fifty ends in the engine's 10 s handshake time-out instead of a result (2 of 96 runs of
+        # ex_cyl_256x128 on 4 slabs, profiles/r02_shared_device_timeouts.txt).  The time-out is reported, never a wrong result: run once more.
+        print("NOTE: handshake time-out with slabs sharing one device, running once more:", (r.stdout + r.stderr)[-300:])
+        r = subprocess.run(cmd, cwd=cwd, env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     m = re.search(r"SHIM_RESULT (.*)", r.stdout)
     assert m, r.stdout[-2000:]
